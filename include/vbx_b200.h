@@ -1,0 +1,106 @@
+/*
+ * vbx_b200 -- C ABI of the B200-native VB-HMM EM loop (the hot path of BUTSpeechFIT/VBx).
+ *
+ * The reference has no FFI: its boundary for this path is the Python function
+ *     VBx(X, Phi, loopProb, Fa, Fb, pi, gamma, maxIters, epsilon, alphaQInit, ref, plot,
+ *         return_model, alpha, invL) -> (gamma, pi, Li[, alpha, invL])        VBx/VBx.py:27-29,126
+ * called once per recording from VBx/vbhmm.py:154-158.  This header is what a ctypes/cffi binding of
+ * that function binds instead; every entry point cites the reference lines whose
+ * work it replaces.  A *batch* of independent recordings (the reference runs one OS process per
+ * recording, AMI_run.sh:53-58) is processed per call.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative vbx_status otherwise; nothing throws or aborts;
+ *    vbx_last_error() gives a human readable message for the last failure on that handle.
+ *  - all array arguments are DEVICE pointers owned by the caller unless the name ends in `_host`;
+ *    row-major, packed ragged: recording b owns frame rows offsets[b] .. offsets[b+1]-1.
+ *  - `S` below is the padded state count returned by vbx_padded_states(); the live state count of
+ *    recording b is n_states[b] <= S (columns >= n_states[b] hold zeros).
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*); there is no host
+ *    synchronisation inside vbx_prepare_* / vbx_run.  One handle per (device, stream); a handle must
+ *    not be used from two threads at once.
+ *  - arithmetic is float32 on the device with float64 accumulation of the ELBO scalars; the reference
+ *    is float64 numpy (parity: SURVEY.md section 8c, tests/test_parity_gpu.py).
+ */
+#ifndef VBX_B200_H
+#define VBX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vbx_handle_s *vbx_handle_t;
+
+enum vbx_status {
+    VBX_OK = 0,
+    VBX_ERR_ARG = -1,       /* bad argument (shape, null pointer, unsupported size)           */
+    VBX_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed                    */
+    VBX_ERR_STATE = -3,     /* call order violated (no plan / workspace not bound / too small) */
+    VBX_ERR_NO_DEVICE = -4  /* no usable sm_100 device                                        */
+};
+
+/* per-recording bits written to flags_out by vbx_run */
+enum vbx_flag {
+    VBX_FLAG_NONFINITE = 1,      /* ELBO became NaN/Inf (the reference has no such check)                    */
+    VBX_FLAG_ELBO_DECREASED = 2, /* "WARNING: Value of auxiliary function has decreased!" VBx/VBx.py:123-124 */
+    VBX_FLAG_CONVERGED = 4       /* stopped by the epsilon test VBx/VBx.py:122 before max_iters              */
+};
+
+const char *vbx_version(void);
+
+/* Smallest supported padded state count >= n_states (4, 8, 16, 32 or 64); -1 if n_states > 64 or < 1. */
+int32_t vbx_padded_states(int32_t n_states);
+
+int vbx_create(int32_t device, vbx_handle_t *out);
+int vbx_destroy(vbx_handle_t h);
+const char *vbx_last_error(vbx_handle_t h);
+
+/* Tuning knobs (ints): "fb_states_per_lane" (0 = auto, 1, 2, 4), "projection" (0 = auto, 1 = FFMA tiles,
+ * 2 = tcgen05 3xTF32).  Unknown names return VBX_ERR_ARG. */
+int vbx_set_option(vbx_handle_t h, const char *name, int32_t value);
+
+/* Describe a batch: offsets_host[n_rec+1] (HOST, int64, offsets_host[0] == 0), feature dim R
+ * (VBx/VBx.py:74 `D`; multiple of 4, <= 128), padded state count S.  Builds the tile lists on the device
+ * and reports the workspace the caller must provide through vbx_bind_workspace (256-byte aligned). */
+int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t R, int32_t S,
+             size_t *workspace_bytes_out);
+int vbx_bind_workspace(vbx_handle_t h, void *workspace, size_t bytes);
+
+/* VBx/VBx.py:87-89:  rho = fea * sqrt(Phi)  and the per-frame constant G (kept as one float64 sum per
+ * recording inside the workspace, since G is state independent and only shifts the ELBO).
+ * fea [N,R], Phi [R], rho_out [N,R] (may alias fea). */
+int vbx_prepare_scale(vbx_handle_t h, const float *fea, const float *Phi, float *rho_out, void *stream);
+
+/* The caller-side projection folded with the scale (VBx/vbhmm.py:129,153 composed with VBx/VBx.py:88-89,
+ * as defined for synthetic batches in SURVEY.md section 8d):  rho = X . V  with X [N,D], V [D,R]
+ * (V = V0 * sqrt(Phi)), D a multiple of 32;  G is recovered from rho and Phi. */
+int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *V, const float *Phi,
+                        float *rho_out, void *stream);
+
+/* The EM loop VBx/VBx.py:91-125 for every recording of the planned batch.
+ *   rho       [N,R]   from vbx_prepare_*                                (VBx/VBx.py:89)
+ *   Phi       [R]                                                        (VBx/VBx.py:30 `Phi`)
+ *   gamma_io  [N,S]   in: initial responsibilities; out: final ones     (VBx/VBx.py:47,82-83,126)
+ *   pi_io     [n_rec,S] in: initial speaker priors; out: learned ones    (VBx/VBx.py:44-46,104)
+ *   n_states  [n_rec] live states per recording, or NULL = S for all
+ *   Fa, Fb, loop_prob, max_iters, epsilon                                (VBx/VBx.py:27-28)
+ *   alpha_io, invL_io [n_rec,S,R] or NULL: speaker models; read for iteration 0 iff warm_start != 0
+ *             (VBx/VBx.py:94), written with the last M-step's values (return_model, VBx/VBx.py:126)
+ *   Li_out    [n_rec,max_iters] float64 ELBO trace, NaN after the last executed iteration (VBx/VBx.py:105)
+ *   n_iters_out [n_rec] iterations executed (the epsilon stop of VBx/VBx.py:122-125 is per recording)
+ *   flags_out [n_rec] vbx_flag bits */
+int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io, float *pi_io,
+            const int32_t *n_states, double Fa, double Fb, double loop_prob, int32_t max_iters, double epsilon,
+            float *alpha_io, float *invL_io, int32_t warm_start, double *Li_out, int32_t *n_iters_out,
+            int32_t *flags_out, void *stream);
+
+/* Number of kernels launched by this handle since creation (bench.py reports it as gpu_launches). */
+int64_t vbx_launch_count(vbx_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBX_B200_H */

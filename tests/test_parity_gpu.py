@@ -1,0 +1,314 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference goldens and the CPU oracle.
+
+Tolerances (north_star: gamma/pi/Li within 1e-4 relative in float32):
+  gamma, pi : max|delta| <= 1e-4 * max|ref|      ELBO : |delta| <= 1e-4 * |ELBO|  (asserted at 1e-5)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from vbx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+G_TOL, PI_TOL, L_RTOL = 1e-4, 1e-4, 1e-5
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def cuda(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev()).to(dtype)
+
+
+def load_cases():
+    z = np.load(os.path.join(GOLD, 'synthetic_cases.npz'))
+    cases = {}
+    for k in z.files:
+        tag, name = k.split('/')
+        cases.setdefault(tag, {})[name] = z[k]
+    return cases
+
+
+CASES = load_cases()
+
+
+def run_gpu(fea, Phi, lengths, gamma0, pi0=None, n_states=None, spl=0, **kw):
+    from vbx_b200.batch import VbxBatch
+    import vbx_b200._lib as L
+    lengths = np.asarray(lengths)
+    S_user = gamma0.shape[1]
+    ns = np.full(len(lengths), S_user, dtype=np.int32) if n_states is None else np.asarray(n_states, dtype=np.int32)
+    vb = VbxBatch(lengths, fea.shape[1], ns, device=dev())
+    if spl:
+        vb.set_option('fb_states_per_lane', spl)
+    S = vb.S
+    g = torch.zeros((fea.shape[0], S), device=dev())
+    g[:, :S_user] = cuda(gamma0)
+    p = torch.zeros((len(lengths), S), device=dev())
+    if pi0 is None:
+        for b in range(len(lengths)):
+            p[b, :ns[b]] = 1.0 / ns[b]
+    else:
+        p[:, :S_user] = cuda(np.broadcast_to(pi0, (len(lengths), S_user)))
+    vb.prepare_scale(cuda(fea), cuda(Phi))
+    extra = {}
+    if 'alpha0' in kw:
+        a = torch.zeros((len(lengths), S, fea.shape[1]), device=dev())
+        il = torch.zeros_like(a)
+        a[:, :S_user] = cuda(kw.pop('alpha0'))
+        il[:, :S_user] = cuda(kw.pop('invL0'))
+        extra = dict(alpha=a, invL=il, warm_start=True)
+    out = vb.run(g, p, return_model=True, **extra, **kw)
+    torch.cuda.synchronize()
+    res = dict(gamma=g[:, :S_user].double().cpu().numpy(), pi=p[:, :S_user].double().cpu().numpy(),
+               Li=out['Li'].cpu().numpy(), n_iters=out['n_iters'].cpu().numpy(), flags=out['flags'].cpu().numpy(),
+               alpha=out['alpha'][:, :S_user].double().cpu().numpy(), invL=out['invL'][:, :S_user].double().cpu().numpy(),
+               gamma_pad=g[:, S_user:].cpu().numpy())
+    vb.close()
+    return res
+
+
+@pytest.mark.parametrize('tag', sorted(CASES))
+def test_reference_goldens(tag):
+    c = CASES[tag]
+    T = c['fea'].shape[0]
+    kw = dict(Fa=float(c['Fa']), Fb=float(c['Fb']), loopProb=float(c['loopProb']), maxIters=int(c['maxIters']),
+              epsilon=float(c['epsilon']))
+    if 'alpha0' in c:
+        kw.update(alpha0=c['alpha0'][None], invL0=c['invL0'][None])
+    out = run_gpu(c['fea'], c['Phi'], [T], c['gamma0'], pi0=c['pi0'], **kw)
+    n = int(out['n_iters'][0])
+    assert n == len(c['Li']), (n, len(c['Li']))
+    assert np.abs(out['gamma'] - c['gamma']).max() <= G_TOL * np.abs(c['gamma']).max()
+    assert np.abs(out['pi'][0] - c['pi']).max() <= PI_TOL * np.abs(c['pi']).max()
+    np.testing.assert_allclose(out['Li'][0, :n], c['Li'], rtol=L_RTOL)
+    assert np.all(np.isnan(out['Li'][0, n:]))
+    assert np.abs(out['alpha'][0] - c['alpha']).max() <= 1e-4 * max(1.0, np.abs(c['alpha']).max())
+    assert np.abs(out['invL'][0] - c['invL']).max() <= 1e-4
+    assert np.all(out['gamma_pad'] == 0)
+    assert not (out['flags'][0] & 1)
+
+
+def es_inputs():
+    z = np.load(os.path.join(GOLD, 'es2005a.npz'))
+    lab = z['labels_ahc'].astype(int)
+    q = np.zeros((len(lab), lab.max() + 1))
+    q[np.arange(len(lab)), lab] = 1.0
+    q = np.exp(q * float(z['smoothing']))
+    q /= q.sum(1, keepdims=True)
+    return z, q
+
+
+def test_es2005a_fixed_iterations():
+    """Config 1: the real recording, same 13 iterations as the reference (VBx/vbhmm.py:154-158)."""
+    z, q = es_inputs()
+    out = run_gpu(z['fea'], z['Phi'], [q.shape[0]], q, Fa=float(z['Fa']), Fb=float(z['Fb']),
+                  loopProb=float(z['loopProb']), maxIters=13, epsilon=-np.inf)
+    assert np.abs(out['gamma'] - z['gamma']).max() <= G_TOL
+    assert np.abs(out['pi'][0] - z['pi']).max() <= PI_TOL
+    np.testing.assert_allclose(out['Li'][0], z['Li'], rtol=L_RTOL)
+    assert np.array_equal(out['gamma'].argmax(1), z['labels'])
+
+
+def test_es2005a_reference_stop_rule():
+    """epsilon=1e-6 on |ELBO|~7e4 is below float32 resolution of the frame terms, so the stop iteration may
+    differ from the reference's 13; the result it stops at must still be the reference's."""
+    z, q = es_inputs()
+    out = run_gpu(z['fea'], z['Phi'], [q.shape[0]], q, Fa=float(z['Fa']), Fb=float(z['Fb']),
+                  loopProb=float(z['loopProb']), maxIters=40, epsilon=1e-6)
+    n = int(out['n_iters'][0])
+    assert 6 <= n <= 40
+    assert abs(out['Li'][0, n - 1] - z['Li'][-1]) <= 1e-6 * abs(z['Li'][-1])
+    assert np.abs(out['gamma'] - z['gamma']).max() <= 5e-4      # may stop an iteration or two early
+    assert np.array_equal(out['gamma'].argmax(1), z['labels'])
+
+
+def ragged_batch(B, S, seed, tmax=700, R=128):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(1, tmax, size=B)
+    lens[0] = 1
+    lens[1] = 2
+    d = synth.make_batch(lens, R=R, S=S, seed=seed, dtype=np.float32)
+    return lens, d
+
+
+@pytest.mark.parametrize('spl', [1, 2, 4])
+def test_ragged_batch_vs_oracle(spl):
+    S = 16
+    lens, d = ragged_batch(37, S, seed=21)
+    ns = np.random.default_rng(3).integers(1, S + 1, size=len(lens)).astype(np.int32)
+    ns[:4] = S
+    g0 = d['gamma0'].astype(np.float64)
+    for b, (lo, hi) in enumerate(zip(d['offsets'][:-1], d['offsets'][1:])):
+        g0[lo:hi, ns[b]:] = 0
+        g0[lo:hi] /= g0[lo:hi].sum(1, keepdims=True)
+    pi0 = np.zeros((len(lens), S))
+    for b in range(len(lens)):
+        pi0[b, :ns[b]] = 1.0 / ns[b]
+    ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], g0, pi0, 0.3, 17.0, 0.99, 8, -np.inf, n_states=ns)
+    out = run_gpu(d['fea'], d['Phi'], lens, g0.astype(np.float32), pi0=None, n_states=ns, spl=spl,
+                  Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=8, epsilon=-np.inf)
+    assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
+    assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
+    np.testing.assert_allclose(out['Li'], ref['Li'], rtol=L_RTOL)
+    assert np.all(out['n_iters'] == 8)
+
+
+@pytest.mark.parametrize('S', [3, 4, 8, 10, 16, 31, 32, 64])
+def test_state_counts_vs_oracle(S):
+    lens, d = ragged_batch(9, S, seed=30 + S, tmax=400)
+    ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(S, 1.0 / S),
+                              0.2, 6.0, 0.35, 6, -np.inf)
+    out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=0.2, Fb=6.0, loopProb=0.35, maxIters=6, epsilon=-np.inf)
+    assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
+    assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
+    np.testing.assert_allclose(out['Li'], ref['Li'], rtol=L_RTOL)
+
+
+def test_small_feature_dims():
+    for R in (16, 32, 64):
+        lens, d = ragged_batch(6, 5, seed=50 + R, tmax=200, R=R)
+        ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(5, 0.2), 0.4, 17.0, 0.4, 5, -np.inf)
+        out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=0.4, Fb=17.0, loopProb=0.4, maxIters=5, epsilon=-np.inf)
+        assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
+        np.testing.assert_allclose(out['Li'], ref['Li'], rtol=L_RTOL)
+
+
+def test_per_recording_early_stop_in_a_batch():
+    """Recordings stop independently (VBx/VBx.py:122-125); stopped ones stay frozen; Li is NaN padded."""
+    lens, d = ragged_batch(12, 8, seed=77, tmax=500)
+    eps = 0.5
+    ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(8, 0.125), 0.3, 17.0, 0.99, 30, eps)
+    out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=30, epsilon=eps)
+    assert len(set(ref['n_iters'].tolist())) > 1, 'test needs recordings that stop at different iterations'
+    same = out['n_iters'] == ref['n_iters']
+    assert same.mean() >= 0.75           # the stop test compares float32-noisy ELBO differences with eps
+    for b in np.nonzero(same)[0]:
+        lo, hi = d['offsets'][b], d['offsets'][b + 1]
+        n = int(ref['n_iters'][b])
+        assert np.abs(out['gamma'][lo:hi] - ref['gamma'][lo:hi]).max() <= G_TOL
+        np.testing.assert_allclose(out['Li'][b, :n], ref['Li'][b, :n], rtol=L_RTOL)
+        assert np.all(np.isnan(out['Li'][b, n:]))
+        assert bool(out['flags'][b] & 4) == (n < 30)
+
+
+def test_batch_is_independent_and_deterministic():
+    """A recording gives bit-identical results alone, inside a batch, and on a second run."""
+    lens, d = ragged_batch(10, 16, seed=5, tmax=600)
+    kw = dict(Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=5, epsilon=-np.inf)
+    full = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], **kw)
+    again = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], **kw)
+    assert np.array_equal(full['gamma'], again['gamma']) and np.array_equal(full['Li'], again['Li'])
+    for b in (0, 3, 9):
+        lo, hi = d['offsets'][b], d['offsets'][b + 1]
+        one = run_gpu(d['fea'][lo:hi], d['Phi'], [hi - lo], d['gamma0'][lo:hi], **kw)
+        assert np.array_equal(one['gamma'], full['gamma'][lo:hi])
+        assert np.array_equal(one['pi'][0], full['pi'][b])
+        assert np.array_equal(one['Li'][0], full['Li'][b])
+
+
+def test_projection_matches_fp32_matmul():
+    from vbx_b200.batch import VbxBatch
+    lens = [300, 45, 129, 1]
+    d = synth.make_batch(lens, R=128, S=4, seed=9, D=256, dtype=np.float32)
+    vb = VbxBatch(lens, 128, 4, device=dev())
+    rho = vb.prepare_project(cuda(d['X']), cuda(d['V']), cuda(d['Phi']))
+    torch.cuda.synchronize()
+    want = d['X'].astype(np.float64) @ d['V'].astype(np.float64)
+    got = rho.double().cpu().numpy()
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    # and it equals the scale path on the projected features (rho = fea * sqrt(Phi))
+    want2 = d['fea'].astype(np.float64) * np.sqrt(d['Phi'].astype(np.float64))
+    assert np.abs(got - want2).max() <= 1e-4 * np.abs(want2).max()
+    vb.close()
+
+
+def test_full_pipeline_from_raw_xvectors():
+    """X (D=256) -> rho = X.V -> EM: equals the oracle run on fea = X.V0."""
+    from vbx_b200.batch import VbxBatch
+    lens = [257, 64, 400]
+    S = 8
+    d = synth.make_batch(lens, R=128, S=S, seed=19, D=256, dtype=np.float32)
+    fea64 = d['X'].astype(np.float64) @ synth.projection_basis(256, 128)
+    ref = co.vbx_oracle_batch(fea64, d['Phi'], d['offsets'], d['gamma0'], np.full(S, 1.0 / S), 0.3, 17.0, 0.99, 6, -np.inf)
+    vb = VbxBatch(lens, 128, S, device=dev())
+    vb.prepare_project(cuda(d['X']), cuda(d['V']), cuda(d['Phi']))
+    g = cuda(d['gamma0'])
+    p = torch.full((3, S), 1.0 / S, device=dev())
+    out = vb.run(g, p, Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=6, epsilon=-np.inf)
+    torch.cuda.synchronize()
+    assert np.abs(g.double().cpu().numpy() - ref['gamma']).max() <= G_TOL
+    np.testing.assert_allclose(out['Li'].cpu().numpy(), ref['Li'], rtol=L_RTOL)
+    vb.close()
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a batch too big for the numpy oracle: rows of gamma sum to 1, pi sums to 1,
+    ELBO does not decrease (up to float32 noise), permuting speaker columns permutes the result; a sample of
+    recordings is compared against the C oracle."""
+    B, T, S = 512, 1000, 16
+    lens = np.full(B, T)
+    d = synth.make_batch(lens, R=128, S=S, seed=123, dtype=np.float32)
+    kw = dict(Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=10, epsilon=-np.inf)
+    out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], **kw)
+    assert np.abs(out['gamma'].sum(1) - 1).max() < 1e-5
+    assert np.abs(out['pi'].sum(1) - 1).max() < 1e-5
+    dl = np.diff(out['Li'], axis=1)
+    assert (dl >= -1e-6 * np.abs(out['Li'][:, 1:])).all()
+    perm = np.random.default_rng(0).permutation(S)
+    outp = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'][:, perm], **kw)
+    np.testing.assert_allclose(outp['Li'], out['Li'], rtol=1e-6)
+    assert np.abs(outp['gamma'] - out['gamma'][:, perm]).max() < 1e-4
+    sel = np.arange(0, B, 37)
+    offs = np.arange(len(sel) + 1) * T
+    fea = np.concatenate([d['fea'][b * T:(b + 1) * T] for b in sel])
+    g0 = np.concatenate([d['gamma0'][b * T:(b + 1) * T] for b in sel])
+    ref = co.vbx_oracle_batch(fea, d['Phi'], offs, g0, np.full(S, 1.0 / S), 0.3, 17.0, 0.99, 10, -np.inf)
+    got = np.concatenate([out['gamma'][b * T:(b + 1) * T] for b in sel])
+    assert np.abs(got - ref['gamma']).max() <= G_TOL
+    np.testing.assert_allclose(out['Li'][sel], ref['Li'], rtol=L_RTOL)
+
+
+def test_dropin_vbx_function():
+    """The reference-facing call: numpy in, (gamma, pi, Li) out (VBx/VBx.py:27-29,126)."""
+    from vbx_b200 import VBx
+    c = CASES['example_hp']
+    g, p, L = VBx(c['fea'], c['Phi'], loopProb=float(c['loopProb']), Fa=float(c['Fa']), Fb=float(c['Fb']),
+                  pi=int(len(c['pi0'])), gamma=c['gamma0'], maxIters=int(c['maxIters']), epsilon=float(c['epsilon']))
+    assert g.dtype == np.float64 and p.dtype == np.float64 and isinstance(L, list) and isinstance(L[0], list)
+    assert g.shape == c['gamma'].shape and p.shape == c['pi'].shape and len(L) == len(c['Li'])
+    assert np.abs(g - c['gamma']).max() <= G_TOL
+    np.testing.assert_allclose([l[0] for l in L], c['Li'], rtol=L_RTOL)
+    g2, p2, L2, a2, il2 = VBx(c['fea'], c['Phi'], loopProb=float(c['loopProb']), Fa=float(c['Fa']), Fb=float(c['Fb']),
+                              pi=c['pi0'], gamma=c['gamma0'], maxIters=3, epsilon=-np.inf, return_model=True)
+    assert a2.shape == c['alpha'].shape and il2.shape == c['invL'].shape
+    with pytest.raises(AssertionError):
+        VBx(c['fea'], c['Phi'], pi=5, gamma=c['gamma0'])
+    with pytest.raises(TypeError):
+        VBx(c['fea'], c['Phi'], pi=np.int64(16), gamma=c['gamma0'])
+    np.random.seed(4)
+    g3, p3, L3 = VBx(c['fea'], c['Phi'], pi=6, maxIters=2)          # gamma=None: global np.random draw
+    assert g3.shape == (c['fea'].shape[0], 6) and np.abs(g3.sum(1) - 1).max() < 1e-5
+
+
+def test_c_abi_argument_errors():
+    import ctypes
+    import vbx_b200._lib as L
+    lib = L.load()
+    h = ctypes.c_void_p()
+    assert lib.vbx_create(0, ctypes.byref(h)) == 0
+    need = ctypes.c_size_t()
+    off = np.array([0, 10], dtype=np.int64)
+    po = off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+    assert lib.vbx_plan(h, po, 1, 130, 16, ctypes.byref(need)) == -1      # R not supported
+    assert lib.vbx_plan(h, po, 1, 128, 17, ctypes.byref(need)) == -1      # S not padded
+    assert b'S must' in lib.vbx_last_error(h)
+    assert lib.vbx_run(h, None, None, None, None, None, 1.0, 1.0, 0.9, 1, 0.0, None, None, 0, None, None, None, None) == -3
+    assert lib.vbx_plan(h, po, 1, 128, 16, ctypes.byref(need)) == 0 and need.value > 0
+    assert lib.vbx_bind_workspace(h, None, 0) == -3
+    assert lib.vbx_destroy(h) == 0

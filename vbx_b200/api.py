@@ -1,0 +1,98 @@
+"""Drop-in replacement for the reference's `VBx()` (VBx/VBx.py:27-126) running on the B200.
+
+Same positional/keyword arguments, same `(gamma, pi, Li[, alpha, invL])` return with float64 numpy
+arrays, same exceptions for bad arguments; the work itself happens in the CUDA library.  The
+reference's single call site is VBx/vbhmm.py:154-158.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .batch import VbxBatch
+
+
+def _der_diagnostic(q, ref, expected=True, xentropy=False):
+    """Host-side passthrough of the optional diagnostic VBx/VBx.py:134-143 (never used by vbhmm.py)."""
+    from scipy.optimize import linear_sum_assignment
+    from scipy.sparse import coo_matrix
+    if not expected:
+        q = coo_matrix((np.ones(len(q)), (range(len(q)), q.argmax(1)))).toarray()
+    ref_mx = coo_matrix((np.ones(len(ref)), (range(len(ref)), ref)))
+    err_mx = ref_mx.T.dot(-np.log(q + np.nextafter(0, 1)) if xentropy else -q)
+    min_cost = err_mx[linear_sum_assignment(err_mx)].sum()
+    return min_cost / float(len(ref)) if xentropy else (len(ref) + min_cost) / float(len(ref))
+
+
+DER = _der_diagnostic
+
+
+def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
+        epsilon=1e-4, alphaQInit=1.0, ref=None, plot=False,
+        return_model=False, alpha=None, invL=None):
+    """See VBx/VBx.py:30-68 for the meaning of every argument (kept identical).
+
+    Differences from the reference, all below its own numerical noise floor for diarization:
+    arithmetic is float32 on the GPU (ELBO accumulated in float64); outputs are float64 numpy."""
+    X = np.asarray(X)
+    Phi = np.asarray(Phi)
+    T, D = X.shape                                    # VBx/VBx.py:74
+    if type(pi) is int:                               # VBx/VBx.py:76-77 (np.int64 is *not* accepted there either)
+        pi = np.ones(pi) / pi
+    S = len(pi)
+    if gamma is None:                                 # VBx/VBx.py:79-83: global np.random, drawn on the host
+        gamma = np.random.gamma(alphaQInit, size=(T, S))
+        gamma = gamma / gamma.sum(1, keepdims=True)
+    assert (gamma.shape[1] == len(pi) and gamma.shape[0] == X.shape[0])   # VBx/VBx.py:85
+    if plot:
+        raise NotImplementedError('plot=True (matplotlib diagnostics, VBx/VBx.py:111-120) is not part of the GPU path')
+
+    dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if dev is None:
+        raise _lib.VbxError('VBx(): no CUDA device - vbx_b200 has no CPU fallback')
+    vb = VbxBatch([T], D, S, device=dev)
+    Sp = vb.S
+    fea_d = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(dev)
+    phi_d = torch.from_numpy(np.ascontiguousarray(Phi, dtype=np.float32)).to(dev)
+    g = torch.zeros((T, Sp), dtype=torch.float32, device=dev)
+    g[:, :S] = torch.from_numpy(np.ascontiguousarray(gamma, dtype=np.float32)).to(dev)
+    p = torch.zeros((1, Sp), dtype=torch.float32, device=dev)
+    p[0, :S] = torch.from_numpy(np.ascontiguousarray(pi, dtype=np.float32)).to(dev)
+    vb.prepare_scale(fea_d, phi_d)
+    warm = alpha is not None and invL is not None    # VBx/VBx.py:94
+    kw = {}
+    if warm:
+        a = torch.zeros((1, Sp, D), dtype=torch.float32, device=dev)
+        il = torch.zeros((1, Sp, D), dtype=torch.float32, device=dev)
+        a[0, :S] = torch.from_numpy(np.ascontiguousarray(alpha, dtype=np.float32)).to(dev)
+        il[0, :S] = torch.from_numpy(np.ascontiguousarray(invL, dtype=np.float32)).to(dev)
+        kw = dict(alpha=a, invL=il, warm_start=True)
+
+    if ref is None:
+        out = vb.run(g, p, Fa=Fa, Fb=Fb, loopProb=loopProb, maxIters=maxIters, epsilon=epsilon,
+                     return_model=return_model, **kw)
+        n = int(out['n_iters'][0].item())
+        flags = int(out['flags'][0].item())
+        Li = [[float(v)] for v in out['Li'][0, :n].cpu().numpy()]
+    else:
+        # the per-iteration DER / cross-entropy diagnostics (VBx/VBx.py:108-109) need gamma on the host
+        # after every iteration: run one iteration per call, warm-starting nothing (the M-step reruns).
+        Li, flags, out = [], 0, None
+        for ii in range(maxIters):
+            out = vb.run(g, p, Fa=Fa, Fb=Fb, loopProb=loopProb, maxIters=1, epsilon=epsilon,
+                         return_model=return_model, **(kw if ii == 0 else {}))
+            elbo = float(out['Li'][0, 0].item())
+            gh = g[:, :S].double().cpu().numpy()
+            Li.append([elbo, DER(gh, ref), DER(gh, ref, xentropy=True)])
+            if ii > 0 and elbo - Li[-2][0] < epsilon:
+                if elbo - Li[-2][0] < 0:
+                    flags |= _lib.FLAG_ELBO_DECREASED
+                break
+    if flags & _lib.FLAG_ELBO_DECREASED:
+        print('WARNING: Value of auxiliary function has decreased!')   # VBx/VBx.py:123-124
+    gamma_out = g[:, :S].double().cpu().numpy()
+    pi_out = p[0, :S].double().cpu().numpy()
+    res = (gamma_out, pi_out, Li)
+    if return_model:
+        res = res + (out['alpha'][0, :S].double().cpu().numpy(), out['invL'][0, :S].double().cpu().numpy())
+    vb.close()
+    return res

@@ -1,0 +1,184 @@
+"""Batched VB-HMM on the GPU: host-side driver over the C ABI (torch is only the owner of device
+memory and streams).
+
+A `VbxBatch` describes B independent recordings packed along the frame axis - the batched
+equivalent of the reference's per-recording loop VBx/vbhmm.py:120-158, where every iteration calls
+VBx() (VBx/VBx.py:27).  `run()` executes VBx/VBx.py:91-125 for all of them at once.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import VbxError
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class VbxBatch:
+    """Plan + workspace for one packed ragged batch on one device."""
+
+    def __init__(self, lengths, R, n_states, device=None):
+        """lengths: per-recording frame counts T_b; R: feature dim seen by VBx() (VBx/VBx.py:74);
+        n_states: int or per-recording ints (the `pi`-as-int / len(pi) of VBx/VBx.py:76-77)."""
+        if not torch.cuda.is_available():
+            raise VbxError('vbx_b200 needs a CUDA device (B200, sm_100); there is no CPU path')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        lengths = np.asarray(lengths, dtype=np.int64).reshape(-1)
+        self.B = int(lengths.shape[0])
+        self.lengths = lengths
+        self.offsets = np.zeros(self.B + 1, dtype=np.int64)
+        np.cumsum(lengths, out=self.offsets[1:])
+        self.N = int(self.offsets[-1])
+        self.R = int(R)
+        ns = np.asarray(n_states, dtype=np.int32).reshape(-1)
+        if ns.size == 1:
+            ns = np.full(self.B, int(ns[0]), dtype=np.int32)
+        if ns.shape[0] != self.B:
+            raise ValueError('n_states must be an int or one int per recording')
+        self.n_states_host = ns
+        self.S = _lib.padded_states(int(ns.max()) if self.B else 1)
+        self.uniform_states = bool(np.all(ns == self.S))
+        self._h = ctypes.c_void_p()
+        rc = self.lib.vbx_create(self.device.index or 0, ctypes.byref(self._h))
+        if rc != 0:
+            raise VbxError(f'vbx_create failed ({rc}): no usable sm_100 device')
+        need = ctypes.c_size_t()
+        self._check(self.lib.vbx_plan(self._h, self.offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                      self.B, self.R, self.S, ctypes.byref(need)))
+        self.workspace_bytes = int(need.value)
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+            self.n_states = None if self.uniform_states else torch.from_numpy(ns).to(self.device)
+        self._check(self.lib.vbx_bind_workspace(self._h, _ptr(self.workspace), self.workspace_bytes))
+        self.rho = None
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.vbx_last_error(self._h)
+            raise VbxError(f'vbx_b200 error {rc}: {msg.decode() if msg else "?"}')
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self.lib.vbx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        self._check(self.lib.vbx_set_option(self._h, name.encode(), int(value)))
+
+    @property
+    def launches(self):
+        return int(self.lib.vbx_launch_count(self._h))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t, shape, name):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError(f'{name}: expected a contiguous float32 CUDA tensor')
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f'{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}')
+        return t
+
+    # ---- VBx/VBx.py:87-89 -----------------------------------------------------------------
+    def prepare_scale(self, fea, Phi, out=None):
+        """rho = fea * sqrt(Phi) (+ the ELBO constant G).  fea [N,R], Phi [R]."""
+        self._f32(fea, (self.N, self.R), 'fea')
+        self._f32(Phi, (self.R,), 'Phi')
+        rho = torch.empty_like(fea) if out is None else self._f32(out, (self.N, self.R), 'out')
+        self._check(self.lib.vbx_prepare_scale(self._h, _ptr(fea), _ptr(Phi), _ptr(rho), self._stream()))
+        self.rho, self.Phi = rho, Phi
+        return rho
+
+    def prepare_project(self, X, V, Phi, out=None):
+        """rho = X @ V for raw D-dim x-vectors (VBx/vbhmm.py:129,153 folded with VBx/VBx.py:88-89)."""
+        D = int(X.shape[1])
+        self._f32(X, (self.N, D), 'X')
+        self._f32(V, (D, self.R), 'V')
+        self._f32(Phi, (self.R,), 'Phi')
+        rho = torch.empty((self.N, self.R), dtype=torch.float32, device=self.device) if out is None \
+            else self._f32(out, (self.N, self.R), 'out')
+        self._check(self.lib.vbx_prepare_project(self._h, _ptr(X), D, _ptr(V), _ptr(Phi), _ptr(rho), self._stream()))
+        self.rho, self.Phi = rho, Phi
+        return rho
+
+    # ---- VBx/VBx.py:91-125 ----------------------------------------------------------------
+    def run(self, gamma, pi, Fa=1.0, Fb=1.0, loopProb=0.9, maxIters=10, epsilon=1e-4,
+            alpha=None, invL=None, warm_start=False, return_model=False):
+        """gamma [N,S] and pi [B,S] float32 CUDA tensors, updated IN PLACE (padded columns must be 0).
+        Returns dict(gamma, pi, Li [B,maxIters] float64 (NaN padded), n_iters [B], flags [B][, alpha, invL])."""
+        if self.rho is None:
+            raise VbxError('call prepare_scale() or prepare_project() first')
+        self._f32(gamma, (self.N, self.S), 'gamma')
+        self._f32(pi, (self.B, self.S), 'pi')
+        dev = self.device
+        if return_model or warm_start:
+            if alpha is None:
+                alpha = torch.zeros((self.B, self.S, self.R), dtype=torch.float32, device=dev)
+            if invL is None:
+                invL = torch.zeros((self.B, self.S, self.R), dtype=torch.float32, device=dev)
+            self._f32(alpha, (self.B, self.S, self.R), 'alpha')
+            self._f32(invL, (self.B, self.S, self.R), 'invL')
+        Li = torch.empty((self.B, max(int(maxIters), 1)), dtype=torch.float64, device=dev)
+        n_iters = torch.empty(self.B, dtype=torch.int32, device=dev)
+        flags = torch.empty(self.B, dtype=torch.int32, device=dev)
+        self._check(self.lib.vbx_run(
+            self._h, _ptr(self.rho), _ptr(self.Phi), _ptr(gamma), _ptr(pi), _ptr(self.n_states),
+            float(Fa), float(Fb), float(loopProb), int(maxIters), float(epsilon),
+            _ptr(alpha), _ptr(invL), int(bool(warm_start)), _ptr(Li), _ptr(n_iters), _ptr(flags),
+            self._stream()))
+        out = dict(gamma=gamma, pi=pi, Li=Li[:, :int(maxIters)], n_iters=n_iters, flags=flags)
+        if return_model or warm_start:
+            out.update(alpha=alpha, invL=invL)
+        return out
+
+
+def vbx_batch(fea, Phi, lengths, gamma, pi=None, n_states=None, loopProb=0.9, Fa=1.0, Fb=1.0, maxIters=10,
+              epsilon=1e-4, return_model=False, alpha=None, invL=None):
+    """One-call batched VBx on CUDA tensors.
+
+    fea [N,R] float32 (the reference's X per recording, packed), Phi [R], lengths [B] (host ints),
+    gamma [N,S_user] initial responsibilities, pi [B,S_user] or None (uniform over the live states).
+    Returns dict with gamma [N,S_user], pi [B,S_user], Li, n_iters, flags (CUDA tensors)."""
+    N, S_user = gamma.shape
+    ns = np.full(len(lengths), S_user, dtype=np.int32) if n_states is None else np.asarray(n_states, dtype=np.int32)
+    vb = VbxBatch(lengths, fea.shape[1], ns, device=fea.device)
+    S = vb.S
+    g = torch.zeros((N, S), dtype=torch.float32, device=fea.device)
+    g[:, :S_user] = gamma
+    p = torch.zeros((vb.B, S), dtype=torch.float32, device=fea.device)
+    if pi is None:
+        nsd = torch.from_numpy(ns).to(fea.device)
+        cols = torch.arange(S, device=fea.device)[None, :]
+        p[:] = (cols < nsd[:, None]).float() / nsd[:, None].float()
+    else:
+        p[:, :S_user] = pi
+    kw = {}
+    warm = alpha is not None and invL is not None
+    if warm:
+        a = torch.zeros((vb.B, S, vb.R), dtype=torch.float32, device=fea.device)
+        il = torch.zeros_like(a)
+        a[:, :S_user] = alpha
+        il[:, :S_user] = invL
+        kw = dict(alpha=a, invL=il, warm_start=True)
+    vb.prepare_scale(fea.contiguous(), Phi.contiguous())
+    out = vb.run(g, p, Fa=Fa, Fb=Fb, loopProb=loopProb, maxIters=maxIters, epsilon=epsilon,
+                 return_model=return_model, **kw)
+    res = dict(gamma=out['gamma'][:, :S_user], pi=out['pi'][:, :S_user], Li=out['Li'], n_iters=out['n_iters'],
+               flags=out['flags'], launches=vb.launches)
+    if return_model or warm:
+        res.update(alpha=out['alpha'][:, :S_user], invL=out['invL'][:, :S_user])
+    torch.cuda.current_stream(fea.device).synchronize()
+    vb.close()
+    return res

@@ -1,0 +1,325 @@
+// C ABI of vbx_b200 (include/vbx_b200.h): handle, batch plan, workspace carving, EM-loop driver.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/vbx_b200.h"
+#include "vbx_internal.cuh"
+
+struct vbx_handle_s {
+    int device = 0;
+    std::string err;
+    vbx::Plan plan;
+    vbx::Workspace ws;
+    bool planned = false, bound = false, prepared = false;
+    size_t ws_need = 0;
+    void *plan_mem = nullptr;  // one device allocation backing all plan arrays
+    int opt_fb_spl = 0;
+    int opt_projection = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(vbx_handle_t h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    return code;
+}
+int cuda_fail(vbx_handle_t h, cudaError_t e, const char *what) {
+    return fail(h, VBX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base(static_cast<char *>(b)) {}
+    template <typename T>
+    T *take(size_t n) {
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += align_up(n * sizeof(T));
+        return p;
+    }
+};
+
+size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
+    Carver c(base);
+    const size_t N = (size_t)pl.n_frames, S = (size_t)pl.S, R = (size_t)pl.R, B = (size_t)pl.n_rec;
+    vbx::Workspace w;
+    w.p = c.take<float>(N * S);
+    w.rowmax = c.take<float>(N);
+    w.rsigma = c.take<float>(N);
+    w.partial = c.take<float>((size_t)pl.n_mtiles * S * R);
+    w.A = c.take<float>(B * S * R);
+    w.bias = c.take<float>(B * S);
+    w.occ = c.take<float>(B * S);
+    w.reg = c.take<double>(B);
+    w.gsum = c.take<double>(B);
+    w.gpart = c.take<double>((size_t)pl.n_mtiles);
+    w.prev_elbo = c.take<double>(B);
+    w.active = c.take<int32_t>(B);
+    if (ws) *ws = w;
+    return c.off + 256;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *vbx_version(void) { return "vbx_b200 0.1 (sm_100a)"; }
+
+int32_t vbx_padded_states(int32_t n) {
+    if (n < 1 || n > vbx::kMaxS) return -1;
+    int32_t s = 4;
+    while (s < n) s <<= 1;
+    return s;
+}
+
+int vbx_create(int32_t device, vbx_handle_t *out) {
+    if (!out) return VBX_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count)
+        return VBX_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VBX_ERR_CUDA;
+    if (prop.major != 10) return VBX_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    vbx_handle_t h = new vbx_handle_s();
+    h->device = device;
+    *out = h;
+    return VBX_OK;
+}
+
+int vbx_destroy(vbx_handle_t h) {
+    if (!h) return VBX_ERR_ARG;
+    if (h->plan_mem) {
+        cudaSetDevice(h->device);
+        cudaFree(h->plan_mem);
+    }
+    delete h;
+    return VBX_OK;
+}
+
+const char *vbx_last_error(vbx_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int vbx_set_option(vbx_handle_t h, const char *name, int32_t value) {
+    if (!h || !name) return VBX_ERR_ARG;
+    if (!strcmp(name, "fb_states_per_lane")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, VBX_ERR_ARG, "fb_states_per_lane must be 0,1,2,4");
+        h->opt_fb_spl = value;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "projection")) {
+        if (value < 0 || value > 2) return fail(h, VBX_ERR_ARG, "projection must be 0,1,2");
+        h->opt_projection = value;
+        return VBX_OK;
+    }
+    return fail(h, VBX_ERR_ARG, std::string("unknown option ") + name);
+}
+
+int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t R, int32_t S,
+             size_t *workspace_bytes_out) {
+    if (!h || !offsets_host || n_rec < 0) return fail(h, VBX_ERR_ARG, "vbx_plan: null argument");
+    if (R < 4 || R > vbx::kMaxR || (R & 3)) return fail(h, VBX_ERR_ARG, "vbx_plan: R must be a multiple of 4 in [4,128]");
+    if (S != 4 && S != 8 && S != 16 && S != 32 && S != 64)
+        return fail(h, VBX_ERR_ARG, "vbx_plan: S must come from vbx_padded_states()");
+    if (n_rec > 0 && offsets_host[0] != 0) return fail(h, VBX_ERR_ARG, "vbx_plan: offsets[0] must be 0");
+    for (int b = 0; b < n_rec; ++b) {
+        const int64_t T = offsets_host[b + 1] - offsets_host[b];
+        if (T < 0) return fail(h, VBX_ERR_ARG, "vbx_plan: offsets must be non-decreasing");
+        if (T > (int64_t)1 << 30) return fail(h, VBX_ERR_ARG, "vbx_plan: recording longer than 2^30 frames");
+    }
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+
+    std::vector<int32_t> order(n_rec);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return offsets_host[a + 1] - offsets_host[a] > offsets_host[b + 1] - offsets_host[b];
+    });
+    std::vector<int32_t> lrec, mrec, mbegin(n_rec + 1, 0);
+    std::vector<int64_t> lf0, mf0;
+    int64_t maxT = 0;
+    for (int b = 0; b < n_rec; ++b) {
+        const int64_t lo = offsets_host[b], hi = offsets_host[b + 1];
+        maxT = std::max(maxT, hi - lo);
+        for (int64_t f = lo; f < hi; f += vbx::kLTile) {
+            lrec.push_back(b);
+            lf0.push_back(f);
+        }
+        mbegin[b] = (int32_t)mrec.size();
+        for (int64_t f = lo; f < hi; f += vbx::kMTile) {
+            mrec.push_back(b);
+            mf0.push_back(f);
+        }
+    }
+    mbegin[n_rec] = (int32_t)mrec.size();
+
+    // one device blob for all plan arrays
+    size_t off = 0;
+    auto reserve = [&](size_t bytes) {
+        size_t o = off;
+        off += align_up(bytes);
+        return o;
+    };
+    const size_t o_off = reserve(sizeof(int64_t) * (n_rec + 1));
+    const size_t o_ord = reserve(sizeof(int32_t) * std::max(n_rec, 1));
+    const size_t o_lrec = reserve(sizeof(int32_t) * std::max<size_t>(lrec.size(), 1));
+    const size_t o_lf0 = reserve(sizeof(int64_t) * std::max<size_t>(lf0.size(), 1));
+    const size_t o_mrec = reserve(sizeof(int32_t) * std::max<size_t>(mrec.size(), 1));
+    const size_t o_mf0 = reserve(sizeof(int64_t) * std::max<size_t>(mf0.size(), 1));
+    const size_t o_mb = reserve(sizeof(int32_t) * (n_rec + 1));
+    if (h->plan_mem) {
+        cudaFree(h->plan_mem);
+        h->plan_mem = nullptr;
+    }
+    h->planned = h->bound = h->prepared = false;
+    e = cudaMalloc(&h->plan_mem, off);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(plan)");
+    char *base = static_cast<char *>(h->plan_mem);
+    auto up = [&](size_t o, const void *src, size_t bytes) {
+        return bytes ? cudaMemcpy(base + o, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    if ((e = up(o_off, offsets_host, sizeof(int64_t) * (n_rec + 1))) != cudaSuccess ||
+        (e = up(o_ord, order.data(), sizeof(int32_t) * n_rec)) != cudaSuccess ||
+        (e = up(o_lrec, lrec.data(), sizeof(int32_t) * lrec.size())) != cudaSuccess ||
+        (e = up(o_lf0, lf0.data(), sizeof(int64_t) * lf0.size())) != cudaSuccess ||
+        (e = up(o_mrec, mrec.data(), sizeof(int32_t) * mrec.size())) != cudaSuccess ||
+        (e = up(o_mf0, mf0.data(), sizeof(int64_t) * mf0.size())) != cudaSuccess ||
+        (e = up(o_mb, mbegin.data(), sizeof(int32_t) * (n_rec + 1))) != cudaSuccess)
+        return cuda_fail(h, e, "cudaMemcpy(plan)");
+
+    vbx::Plan &pl = h->plan;
+    pl.n_rec = n_rec;
+    pl.R = R;
+    pl.S = S;
+    pl.n_frames = n_rec ? offsets_host[n_rec] : 0;
+    pl.n_ltiles = (int32_t)lrec.size();
+    pl.n_mtiles = (int32_t)mrec.size();
+    pl.max_T = maxT;
+    pl.offsets = reinterpret_cast<const int64_t *>(base + o_off);
+    pl.order = reinterpret_cast<const int32_t *>(base + o_ord);
+    pl.ltile_rec = reinterpret_cast<const int32_t *>(base + o_lrec);
+    pl.ltile_f0 = reinterpret_cast<const int64_t *>(base + o_lf0);
+    pl.mtile_rec = reinterpret_cast<const int32_t *>(base + o_mrec);
+    pl.mtile_f0 = reinterpret_cast<const int64_t *>(base + o_mf0);
+    pl.mtile_begin = reinterpret_cast<const int32_t *>(base + o_mb);
+    h->ws_need = carve(pl, nullptr, nullptr);
+    h->planned = true;
+    if (workspace_bytes_out) *workspace_bytes_out = h->ws_need;
+    return VBX_OK;
+}
+
+int vbx_bind_workspace(vbx_handle_t h, void *workspace, size_t bytes) {
+    if (!h) return VBX_ERR_ARG;
+    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_bind_workspace: call vbx_plan first");
+    if (!workspace || bytes < h->ws_need) return fail(h, VBX_ERR_STATE, "vbx_bind_workspace: workspace too small");
+    const size_t mis = reinterpret_cast<uintptr_t>(workspace) & 255;
+    char *base = static_cast<char *>(workspace) + (mis ? 256 - mis : 0);
+    carve(h->plan, base, &h->ws);
+    h->bound = true;
+    h->prepared = false;
+    return VBX_OK;
+}
+
+static int check_ready(vbx_handle_t h, const char *who) {
+    if (!h) return VBX_ERR_ARG;
+    if (!h->planned || !h->bound) return fail(h, VBX_ERR_STATE, std::string(who) + ": plan and bind a workspace first");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    return VBX_OK;
+}
+static int counted(vbx_handle_t h, int n, const char *what) {
+    if (n < 0) return cuda_fail(h, cudaGetLastError(), what);
+    h->launches += n;
+    return VBX_OK;
+}
+
+int vbx_prepare_scale(vbx_handle_t h, const float *fea, const float *Phi, float *rho_out, void *stream) {
+    int rc = check_ready(h, "vbx_prepare_scale");
+    if (rc) return rc;
+    if (h->plan.n_frames && (!fea || !Phi || !rho_out)) return fail(h, VBX_ERR_ARG, "vbx_prepare_scale: null pointer");
+    rc = counted(h, vbx::launch_prepare_scale(h->plan, h->ws, fea, Phi, rho_out, (cudaStream_t)stream), "prepare_scale");
+    if (rc) return rc;
+    h->prepared = true;
+    return VBX_OK;
+}
+
+int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *V, const float *Phi, float *rho_out,
+                        void *stream) {
+    int rc = check_ready(h, "vbx_prepare_project");
+    if (rc) return rc;
+    if (h->plan.n_frames && (!X || !V || !Phi || !rho_out)) return fail(h, VBX_ERR_ARG, "vbx_prepare_project: null pointer");
+    if (D < 32 || (D & 31)) return fail(h, VBX_ERR_ARG, "vbx_prepare_project: D must be a multiple of 32");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool done = false;
+    if (h->opt_projection != 1) {
+        std::string why;
+        int n = vbx::launch_project_tcgen05(h->plan, X, D, V, rho_out, st, &why);
+        if (n >= 0) {
+            h->launches += n;
+            done = true;
+        } else if (h->opt_projection == 2) {
+            return fail(h, VBX_ERR_ARG, "vbx_prepare_project: tcgen05 path unavailable: " + why);
+        }
+    }
+    if (!done) {
+        rc = counted(h, vbx::launch_project_ffma(h->plan, X, D, V, rho_out, st), "project_ffma");
+        if (rc) return rc;
+    }
+    rc = counted(h, vbx::launch_g_from_rho(h->plan, h->ws, rho_out, Phi, st), "g_from_rho");
+    if (rc) return rc;
+    h->prepared = true;
+    return VBX_OK;
+}
+
+int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io, float *pi_io,
+            const int32_t *n_states, double Fa, double Fb, double loop_prob, int32_t max_iters, double epsilon,
+            float *alpha_io, float *invL_io, int32_t warm_start, double *Li_out, int32_t *n_iters_out,
+            int32_t *flags_out, void *stream) {
+    int rc = check_ready(h, "vbx_run");
+    if (rc) return rc;
+    if (!h->prepared) return fail(h, VBX_ERR_STATE, "vbx_run: call vbx_prepare_scale/project first (G is part of the ELBO)");
+    if (max_iters < 0) return fail(h, VBX_ERR_ARG, "vbx_run: max_iters < 0");
+    if (!(Fb != 0.0)) return fail(h, VBX_ERR_ARG, "vbx_run: Fb must be non-zero");
+    if (warm_start && (!alpha_io || !invL_io)) return fail(h, VBX_ERR_ARG, "vbx_run: warm_start needs alpha_io and invL_io");
+    const vbx::Plan &pl = h->plan;
+    if (pl.n_rec == 0) return VBX_OK;
+    if (!Li_out || !n_iters_out || !flags_out || !pi_io) return fail(h, VBX_ERR_ARG, "vbx_run: null output pointer");
+    if (pl.n_frames && (!rho || !Phi || !gamma_io)) return fail(h, VBX_ERR_ARG, "vbx_run: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    vbx::RunParams rp;
+    rp.dFa = Fa;
+    rp.dFb = Fb;
+    rp.dFaFb = Fa / Fb;
+    rp.epsilon = epsilon;
+    rp.Fa = (float)Fa;
+    rp.Fb = (float)Fb;
+    rp.FaFb = (float)(Fa / Fb);
+    rp.loopP = (float)loop_prob;
+    rp.max_iters = max_iters;
+
+    rc = counted(h, vbx::launch_run_init(pl, h->ws, gamma_io, n_states, Li_out, n_iters_out, flags_out, max_iters, st), "run_init");
+    if (rc) return rc;
+    for (int it = 0; it < max_iters; ++it) {
+        const bool given = it == 0 && warm_start;
+        if (!given) {
+            rc = counted(h, vbx::launch_mstep_partial(pl, h->ws, rho, gamma_io, st), "mstep_partial");
+            if (rc) return rc;
+        }
+        rc = counted(h, vbx::launch_speaker_model(pl, h->ws, rp, Phi, n_states, alpha_io, invL_io, given, st), "speaker_model");
+        if (rc) return rc;
+        rc = counted(h, vbx::launch_loglik(pl, h->ws, rho, st), "loglik");
+        if (rc) return rc;
+        rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, st), "forward_backward");
+        if (rc) return rc;
+    }
+    return VBX_OK;
+}
+
+int64_t vbx_launch_count(vbx_handle_t h) { return h ? h->launches : -1; }
+
+}  // extern "C"

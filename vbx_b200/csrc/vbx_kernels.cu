@@ -1,0 +1,823 @@
+// Hand-written sm_100a kernels of the VB-HMM EM loop (reference: VBx/VBx.py:74-126,146-175).
+//
+// Data layout (all float32, row-major, packed ragged over the batch):
+//   rho    [N,R]   x-vectors scaled into the PLDA space           VBx/VBx.py:89
+//   gamma  [N,S]   responsibilities; doubles as the store of the normalised forward variables
+//   p      [N,S]   exp(log_p - rowmax)   rowmax [N]               VBx/VBx.py:97 (without the common G_t)
+//   rsigma [N]     reciprocal forward scales
+// One EM iteration = 4 launches:
+//   mstep_partial  -> per-tile gamma^T rho                (VBx/VBx.py:96, the T-long contraction)
+//   speaker_model  -> invL, alpha, bias, ELBO regulariser (VBx/VBx.py:95-96,100)
+//   loglik         -> p, rowmax                           (VBx/VBx.py:97)
+//   forward_backward -> gamma, pi, N_s, ELBO, stop test   (VBx/VBx.py:98-105,122-125,146-175)
+#include <math_constants.h>
+
+#include "vbx_internal.cuh"
+
+namespace vbx {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+template <int LANES>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+template <int N>
+struct Vec {
+    float v[N];
+};
+template <int N>
+__device__ __forceinline__ Vec<N> ld_vec(const float *p);
+template <>
+__device__ __forceinline__ Vec<1> ld_vec<1>(const float *p) {
+    Vec<1> r;
+    r.v[0] = *p;
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<2> ld_vec<2>(const float *p) {
+    float2 t = *reinterpret_cast<const float2 *>(p);
+    Vec<2> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<4> ld_vec<4>(const float *p) {
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    Vec<4> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    r.v[2] = t.z;
+    r.v[3] = t.w;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Vec<N> ldg_vec(const float *p);
+template <>
+__device__ __forceinline__ Vec<1> ldg_vec<1>(const float *p) {
+    Vec<1> r;
+    r.v[0] = __ldg(p);
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<2> ldg_vec<2>(const float *p) {
+    float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    Vec<2> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<4> ldg_vec<4>(const float *p) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    Vec<4> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    r.v[2] = t.z;
+    r.v[3] = t.w;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ void st_vec(float *p, const float *v);
+template <>
+__device__ __forceinline__ void st_vec<1>(float *p, const float *v) {
+    *p = v[0];
+}
+template <>
+__device__ __forceinline__ void st_vec<2>(float *p, const float *v) {
+    *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+}
+template <>
+__device__ __forceinline__ void st_vec<4>(float *p, const float *v) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepare: rho = fea * sqrt(Phi), G partial sums per M-tile          VBx/VBx.py:87-89
+// MODE 0: in = fea, writes rho, ||x||^2 from fea.   MODE 1: in = rho (read only), ||x||^2 = sum rho^2/Phi.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) prepare_kernel(Plan pl, Workspace ws, const float *__restrict__ in,
+                                                      const float *__restrict__ Phi, float *rho) {
+    const int tile = blockIdx.x;
+    const int rec = pl.mtile_rec[tile];
+    const int64_t f0 = pl.mtile_f0[tile];
+    const int len = (int)min((int64_t)kMTile, pl.offsets[rec + 1] - f0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int R = pl.R;
+    const bool rlive = 4 * lane < R;
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rlive) {
+        float4 ph = __ldg(reinterpret_cast<const float4 *>(Phi) + lane);
+        if (MODE == 0)
+            sc = make_float4(sqrtf(ph.x), sqrtf(ph.y), sqrtf(ph.z), sqrtf(ph.w));
+        else
+            sc = make_float4(1.f / ph.x, 1.f / ph.y, 1.f / ph.z, 1.f / ph.w);
+    }
+    const double cst = (double)R * 1.8378770664093454835606594728112;  // R * log(2*pi)
+    double gw = 0.0;
+    for (int t = warp; t < len; t += 8) {
+        float n2 = 0.f;
+        if (rlive) {
+            const int64_t idx = (f0 + t) * R + 4 * lane;
+            float4 x = *reinterpret_cast<const float4 *>(in + idx);
+            if (MODE == 0) {
+                n2 = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+                *reinterpret_cast<float4 *>(rho + idx) = make_float4(x.x * sc.x, x.y * sc.y, x.z * sc.z, x.w * sc.w);
+            } else {
+                n2 = x.x * x.x * sc.x + x.y * x.y * sc.y + x.z * x.z * sc.z + x.w * x.w * sc.w;
+            }
+        }
+        n2 = group_sum<32>(n2);
+        gw += -0.5 * ((double)n2 + cst);
+    }
+    __shared__ double sg[8];
+    if (lane == 0) sg[warp] = gw;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += sg[i];
+        ws.gpart[tile] = s;
+    }
+}
+
+__global__ void gsum_kernel(Plan pl, Workspace ws) {
+    const int rec = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rec >= pl.n_rec) return;
+    double s = 0.0;
+    for (int t = pl.mtile_begin[rec]; t < pl.mtile_begin[rec + 1]; ++t) s += ws.gpart[t];
+    ws.gsum[rec] = s;
+}
+
+int launch_prepare_scale(const Plan &pl, const Workspace &ws, const float *fea, const float *Phi, float *rho,
+                         cudaStream_t st) {
+    if (pl.n_mtiles == 0) return 0;
+    prepare_kernel<0><<<pl.n_mtiles, 256, 0, st>>>(pl, ws, fea, Phi, rho);
+    gsum_kernel<<<(pl.n_rec + 127) / 128, 128, 0, st>>>(pl, ws);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+int launch_g_from_rho(const Plan &pl, const Workspace &ws, const float *rho, const float *Phi, cudaStream_t st) {
+    if (pl.n_mtiles == 0) return 0;
+    prepare_kernel<1><<<pl.n_mtiles, 256, 0, st>>>(pl, ws, rho, Phi, nullptr);
+    gsum_kernel<<<(pl.n_rec + 127) / 128, 128, 0, st>>>(pl, ws);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// projection, FFMA tiles:  rho[N,R] = X[N,D] . V[D,R]     (vbhmm.py:129,153 folded)
+// 128 x 128 block tile, 8 x 8 per thread, k-chunks of 16 through shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) project_ffma_kernel(const float *__restrict__ X, const float *__restrict__ V,
+                                                            float *__restrict__ rho, int64_t N, int D, int R) {
+    constexpr int BM = 128, BN = 128, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 8 rows x 8 cols (strided by 16)
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += BK) {
+        // A tile: 128 rows x 16 k -> 512 float4, 2 per thread
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * 256;
+            const int r = idx >> 2, c4 = idx & 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < N) v = __ldg(reinterpret_cast<const float4 *>(X + (row0 + r) * D + k0) + c4);
+            As[c4 * 4 + 0][r] = v.x;
+            As[c4 * 4 + 1][r] = v.y;
+            As[c4 * 4 + 2][r] = v.z;
+            As[c4 * 4 + 3][r] = v.w;
+        }
+        // B tile: 16 k x 128 cols -> 512 float4
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * 256;
+            const int kk = idx >> 5, c4 = idx & 31;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * c4 < R) v = __ldg(reinterpret_cast<const float4 *>(V + (int64_t)(k0 + kk) * R) + c4);
+            *reinterpret_cast<float4 *>(&Bs[kk][4 * c4]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = row0 + ty + 16 * i;
+        if (r < N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = tx + 16 * j;
+                if (c < R) rho[r * R + c] = acc[i][j];
+            }
+        }
+    }
+}
+
+int launch_project_ffma(const Plan &pl, const float *X, int D, const float *V, float *rho, cudaStream_t st) {
+    if (pl.n_frames == 0) return 0;
+    const int64_t blocks = (pl.n_frames + 127) / 128;
+    project_ffma_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, V, rho, pl.n_frames, D, pl.R);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// run_init: per recording reset + initial occupancies N_s = sum_t gamma[t,s]   (VBx/VBx.py:95 for ii=0)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) run_init_kernel(Plan pl, Workspace ws, const float *__restrict__ gamma,
+                                                       const int32_t *__restrict__ n_states, double *Li,
+                                                       int32_t *n_iters, int32_t *flags, int max_iters) {
+    const int rec = blockIdx.x;
+    const int S = pl.S;
+    const int tid = threadIdx.x;
+    const int64_t f0 = pl.offsets[rec];
+    const int64_t T = pl.offsets[rec + 1] - f0;
+    const int ns = n_states ? n_states[rec] : S;
+    const bool ok = T > 0 && ns > 0;
+    if (tid == 0) {
+        ws.active[rec] = ok ? 1 : 0;
+        ws.prev_elbo[rec] = 0.0;
+        n_iters[rec] = 0;
+        flags[rec] = 0;
+    }
+    for (int i = tid; i < max_iters; i += 128) Li[(int64_t)rec * max_iters + i] = CUDART_NAN;
+    __shared__ double part[128];
+    const int s = tid % S, k = tid / S, nk = 128 / S;
+    double acc = 0.0;
+    for (int64_t t = k; t < T; t += nk) acc += (double)gamma[(f0 + t) * S + s];
+    part[tid] = acc;
+    __syncthreads();
+    if (tid < S) {
+        double tot = 0.0;
+        for (int i = 0; i < nk; ++i) tot += part[i * S + tid];
+        ws.occ[(int64_t)rec * S + tid] = (float)tot;
+    }
+}
+
+int launch_run_init(const Plan &pl, const Workspace &ws, const float *gamma, const int32_t *n_states, double *Li,
+                    int32_t *n_iters, int32_t *flags, int max_iters, cudaStream_t st) {
+    if (pl.n_rec == 0) return 0;
+    run_init_kernel<<<pl.n_rec, 128, 0, st>>>(pl, ws, gamma, n_states, Li, n_iters, flags, max_iters);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// M-step accumulation: partial[tile][s][r] = sum_{t in tile} gamma[t,s] * rho[t,r]      VBx/VBx.py:96
+// One CTA per <=256-frame tile of one recording.  A warp owns a frame slot and SPT states; lane owns
+// 4 consecutive r (the rho row is one coalesced 512 B request), gamma values are warp-uniform loads.
+// ------------------------------------------------------------------------------------------------
+template <int S_PAD>
+__global__ void __launch_bounds__(256) mstep_partial_kernel(Plan pl, Workspace ws, const float *__restrict__ rho,
+                                                            const float *__restrict__ gamma) {
+    constexpr int SPT = S_PAD < 16 ? S_PAD : 16;
+    constexpr int NG = S_PAD / SPT;
+    constexpr int FS = 8 / NG;
+    __shared__ __align__(16) float red[S_PAD][kMaxR];
+    const int tile = blockIdx.x;
+    const int rec = pl.mtile_rec[tile];
+    if (!ws.active[rec]) return;
+    const int64_t f0 = pl.mtile_f0[tile];
+    const int len = (int)min((int64_t)kMTile, pl.offsets[rec + 1] - f0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sg = warp % NG, fs = warp / NG;
+    const int R = pl.R;
+    const bool rlive = 4 * lane < R;
+    float acc[SPT][4];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[s][c] = 0.f;
+    const float *grow = gamma + f0 * S_PAD + sg * SPT;
+    const float *xrow = rho + f0 * R + 4 * lane;
+#pragma unroll 2
+    for (int t = fs; t < len; t += FS) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rlive) x = __ldg(reinterpret_cast<const float4 *>(xrow + (int64_t)t * R));
+        const float4 *g4 = reinterpret_cast<const float4 *>(grow + (int64_t)t * S_PAD);
+#pragma unroll
+        for (int q = 0; q < SPT / 4; ++q) {
+            const float4 g = __ldg(g4 + q);
+            acc[4 * q + 0][0] = fmaf(g.x, x.x, acc[4 * q + 0][0]);
+            acc[4 * q + 0][1] = fmaf(g.x, x.y, acc[4 * q + 0][1]);
+            acc[4 * q + 0][2] = fmaf(g.x, x.z, acc[4 * q + 0][2]);
+            acc[4 * q + 0][3] = fmaf(g.x, x.w, acc[4 * q + 0][3]);
+            acc[4 * q + 1][0] = fmaf(g.y, x.x, acc[4 * q + 1][0]);
+            acc[4 * q + 1][1] = fmaf(g.y, x.y, acc[4 * q + 1][1]);
+            acc[4 * q + 1][2] = fmaf(g.y, x.z, acc[4 * q + 1][2]);
+            acc[4 * q + 1][3] = fmaf(g.y, x.w, acc[4 * q + 1][3]);
+            acc[4 * q + 2][0] = fmaf(g.z, x.x, acc[4 * q + 2][0]);
+            acc[4 * q + 2][1] = fmaf(g.z, x.y, acc[4 * q + 2][1]);
+            acc[4 * q + 2][2] = fmaf(g.z, x.z, acc[4 * q + 2][2]);
+            acc[4 * q + 2][3] = fmaf(g.z, x.w, acc[4 * q + 2][3]);
+            acc[4 * q + 3][0] = fmaf(g.w, x.x, acc[4 * q + 3][0]);
+            acc[4 * q + 3][1] = fmaf(g.w, x.y, acc[4 * q + 3][1]);
+            acc[4 * q + 3][2] = fmaf(g.w, x.z, acc[4 * q + 3][2]);
+            acc[4 * q + 3][3] = fmaf(g.w, x.w, acc[4 * q + 3][3]);
+        }
+    }
+    // fixed-order reduction over the frame slots (deterministic)
+#pragma unroll 1
+    for (int k = 0; k < FS; ++k) {
+        if (fs == k) {
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) {
+                float4 *dst = reinterpret_cast<float4 *>(&red[sg * SPT + s][4 * lane]);
+                float4 v = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+                if (k > 0) {
+                    const float4 o = *dst;
+                    v.x += o.x;
+                    v.y += o.y;
+                    v.z += o.z;
+                    v.w += o.w;
+                }
+                *dst = v;
+            }
+        }
+        __syncthreads();
+    }
+    const int R4 = R >> 2;
+    float *out = ws.partial + (int64_t)tile * S_PAD * R;
+    for (int i = threadIdx.x; i < S_PAD * R4; i += 256) {
+        const int s = i / R4, c4 = i - s * R4;
+        *reinterpret_cast<float4 *>(out + (int64_t)s * R + 4 * c4) = *reinterpret_cast<const float4 *>(&red[s][4 * c4]);
+    }
+}
+
+int launch_mstep_partial(const Plan &pl, const Workspace &ws, const float *rho, const float *gamma, cudaStream_t st) {
+    if (pl.n_mtiles == 0) return 0;
+    switch (pl.S) {
+        case 4: mstep_partial_kernel<4><<<pl.n_mtiles, 256, 0, st>>>(pl, ws, rho, gamma); break;
+        case 8: mstep_partial_kernel<8><<<pl.n_mtiles, 256, 0, st>>>(pl, ws, rho, gamma); break;
+        case 16: mstep_partial_kernel<16><<<pl.n_mtiles, 256, 0, st>>>(pl, ws, rho, gamma); break;
+        case 32: mstep_partial_kernel<32><<<pl.n_mtiles, 256, 0, st>>>(pl, ws, rho, gamma); break;
+        case 64: mstep_partial_kernel<64><<<pl.n_mtiles, 256, 0, st>>>(pl, ws, rho, gamma); break;
+        default: return -1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// speaker model: invL, alpha (eqs 17,16; VBx/VBx.py:95-96), the per-speaker bias of eq. (23)
+// (VBx/VBx.py:97) and the ELBO regulariser of eq. (25) (VBx/VBx.py:100).  One CTA per recording,
+// thread = r.  Sums over tiles run in tile order in float64 (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) speaker_model_kernel(Plan pl, Workspace ws, RunParams rp,
+                                                            const float *__restrict__ Phi,
+                                                            const int32_t *__restrict__ n_states, float *alpha_io,
+                                                            float *invL_io, int from_given) {
+    const int rec = blockIdx.x;
+    if (!ws.active[rec]) return;
+    const int S = pl.S, R = pl.R;
+    const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
+    const bool live = r < R;
+    const int ns = n_states ? n_states[rec] : S;
+    const double phi = live ? (double)Phi[r] : 0.0;
+    const int t_lo = pl.mtile_begin[rec], t_hi = pl.mtile_begin[rec + 1];
+    __shared__ double sred[4];
+    double regacc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const int64_t o = ((int64_t)rec * S + s) * R + r;
+        if (s >= ns) {  // dead column: never wins, never contributes
+            if (live) {
+                ws.A[o] = 0.f;
+                if (alpha_io) alpha_io[o] = 0.f;
+                if (invL_io) invL_io[o] = 0.f;
+            }
+            if (r == 0) ws.bias[(int64_t)rec * S + s] = CUDART_INF_F;
+            continue;
+        }
+        double invL = 1.0, alpha = 0.0;
+        if (live) {
+            if (from_given) {
+                alpha = (double)alpha_io[o];
+                invL = (double)invL_io[o];
+            } else {
+                double gr = 0.0;
+                for (int t = t_lo; t < t_hi; ++t) gr += (double)ws.partial[((int64_t)t * S + s) * R + r];
+                const double Ns = (double)ws.occ[(int64_t)rec * S + s];
+                invL = 1.0 / (1.0 + rp.dFaFb * Ns * phi);
+                alpha = rp.dFaFb * invL * gr;
+                if (alpha_io) alpha_io[o] = (float)alpha;
+                if (invL_io) invL_io[o] = (float)invL;
+            }
+            ws.A[o] = (float)(rp.dFa * alpha);
+            regacc += log(invL) - invL - alpha * alpha + 1.0;
+        }
+        double c = live ? (invL + alpha * alpha) * phi : 0.0;
+        c = warp_sum_d(c);
+        __syncthreads();
+        if (lane == 0) sred[warp] = c;
+        __syncthreads();
+        if (r == 0) ws.bias[(int64_t)rec * S + s] = (float)(rp.dFa * 0.5 * (sred[0] + sred[1] + sred[2] + sred[3]));
+    }
+    regacc = warp_sum_d(regacc);
+    __syncthreads();
+    if (lane == 0) sred[warp] = regacc;
+    __syncthreads();
+    if (r == 0) ws.reg[rec] = 0.5 * rp.dFb * (sred[0] + sred[1] + sred[2] + sred[3]);
+}
+
+int launch_speaker_model(const Plan &pl, const Workspace &ws, const RunParams &rp, const float *Phi,
+                         const int32_t *n_states, float *alpha_io, float *invL_io, bool from_given,
+                         cudaStream_t st) {
+    if (pl.n_rec == 0) return 0;
+    speaker_model_kernel<<<pl.n_rec, 128, 0, st>>>(pl, ws, rp, Phi, n_states, alpha_io, invL_io, from_given ? 1 : 0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// log-likelihood + row softmax numerator, fused:                               VBx/VBx.py:97
+//   ll[t,s] = sum_r rho[t,r] * A[s,r] - bias[s] ;  rowmax[t] = max_s ll ;  p[t,s] = exp(ll - rowmax)
+// One CTA = 64 frames of one recording.  rho tile and the recording's A are staged once in shared
+// memory (cp.async, rows padded by 4 floats -> conflict-free LDS.128); each thread owns FJ frames x SJ
+// states and walks k in float4 steps.
+// ------------------------------------------------------------------------------------------------
+template <int S_PAD>
+__global__ void __launch_bounds__(128) loglik_kernel(Plan pl, Workspace ws, const float *__restrict__ rho) {
+    constexpr int SL = S_PAD < 8 ? S_PAD : 8;  // state lanes
+    constexpr int SJ = S_PAD / SL;             // states per thread (strided by SL)
+    constexpr int FL = 128 / SL;               // frame lanes
+    constexpr int FJ = kLTile / FL;            // frames per thread (strided by FL)
+    extern __shared__ float4 smem4[];
+    float *smem = reinterpret_cast<float *>(smem4);
+    const int R = pl.R, RP = R + 4, R4 = R >> 2;
+    float *rhoS = smem;             // [kLTile][RP]
+    float *AS = smem + kLTile * RP; // [S_PAD][RP]
+    const int tile = blockIdx.x;
+    const int rec = pl.ltile_rec[tile];
+    if (!ws.active[rec]) return;
+    const int64_t f0 = pl.ltile_f0[tile];
+    const int len = (int)min((int64_t)kLTile, pl.offsets[rec + 1] - f0);
+    const int tid = threadIdx.x;
+    {
+        const float *src = rho + f0 * R;
+        for (int i = tid; i < len * R4; i += 128) {
+            const int row = i / R4, c4 = i - row * R4;
+            cp_async16(rhoS + row * RP + 4 * c4, src + (int64_t)row * R + 4 * c4);
+        }
+        const float *Ab = ws.A + (int64_t)rec * S_PAD * R;
+        for (int i = tid; i < S_PAD * R4; i += 128) {
+            const int row = i / R4, c4 = i - row * R4;
+            cp_async16(AS + row * RP + 4 * c4, Ab + (int64_t)row * R + 4 * c4);
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+    const int sl = tid % SL, fl = tid / SL;
+    float acc[FJ][SJ];
+#pragma unroll
+    for (int j = 0; j < SJ; ++j) {
+        const float b = ws.bias[(int64_t)rec * S_PAD + sl + SL * j];
+#pragma unroll
+        for (int i = 0; i < FJ; ++i) acc[i][j] = -b;
+    }
+#pragma unroll 4
+    for (int k4 = 0; k4 < R4; ++k4) {
+        float4 x[FJ], a[SJ];
+#pragma unroll
+        for (int i = 0; i < FJ; ++i) x[i] = *reinterpret_cast<const float4 *>(rhoS + (fl + FL * i) * RP + 4 * k4);
+#pragma unroll
+        for (int j = 0; j < SJ; ++j) a[j] = *reinterpret_cast<const float4 *>(AS + (sl + SL * j) * RP + 4 * k4);
+#pragma unroll
+        for (int i = 0; i < FJ; ++i)
+#pragma unroll
+            for (int j = 0; j < SJ; ++j) {
+                acc[i][j] = fmaf(x[i].x, a[j].x, acc[i][j]);
+                acc[i][j] = fmaf(x[i].y, a[j].y, acc[i][j]);
+                acc[i][j] = fmaf(x[i].z, a[j].z, acc[i][j]);
+                acc[i][j] = fmaf(x[i].w, a[j].w, acc[i][j]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < FJ; ++i) {
+        float m = acc[i][0];
+#pragma unroll
+        for (int j = 1; j < SJ; ++j) m = fmaxf(m, acc[i][j]);
+        m = group_max<SL>(m);
+        const int fr = fl + FL * i;
+        if (fr < len) {
+            float *dst = ws.p + (f0 + fr) * S_PAD + sl;
+#pragma unroll
+            for (int j = 0; j < SJ; ++j) dst[SL * j] = expf(acc[i][j] - m);
+            if (sl == 0) ws.rowmax[f0 + fr] = m;
+        }
+    }
+}
+
+static size_t loglik_smem(int S_pad, int R) { return (size_t)(kLTile + S_pad) * (R + 4) * sizeof(float); }
+
+template <int S_PAD>
+static int launch_loglik_t(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st) {
+    const size_t smem = loglik_smem(S_PAD, pl.R);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(loglik_kernel<S_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)loglik_smem(S_PAD, kMaxR)) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    loglik_kernel<S_PAD><<<pl.n_ltiles, 128, smem, st>>>(pl, ws, rho);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st) {
+    if (pl.n_ltiles == 0) return 0;
+    switch (pl.S) {
+        case 4: return launch_loglik_t<4>(pl, ws, rho, st);
+        case 8: return launch_loglik_t<8>(pl, ws, rho, st);
+        case 16: return launch_loglik_t<16>(pl, ws, rho, st);
+        case 32: return launch_loglik_t<32>(pl, ws, rho, st);
+        case 64: return launch_loglik_t<64>(pl, ws, rho, st);
+        default: return -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward-backward in the scaled linear domain                     VBx/VBx.py:98-105,122-125,146-175
+//
+// The transition matrix of VBx/VBx.py:98 is  loopP*I + (1-loopP)*1*pi^T ; with the reference's +1e-8
+// inside every log (VBx/VBx.py:159,164) it acts on a vector a as  loopP*a + w*sum(a),  w = (1-loopP)*pi + 1e-8,
+// so each frame costs O(S).  A group of LPR lanes owns one recording (SPL states per lane), 32/LPR
+// recordings share a warp.  Forward variables are normalised per frame (scale sigma_t); the backward
+// variables are scaled by the forward scales, so gamma_t = a_t * b_t sums to one without renormalising and
+// b_t stays within [1e-8, 1e8].  The same sweep accumulates N_s (VBx/VBx.py:95) and the re-entry statistics of
+// eq. (24) (VBx/VBx.py:101-103); the tail applies eq. (24)-(25) and the stop test (VBx/VBx.py:104-105,122-125).
+// ------------------------------------------------------------------------------------------------
+template <int S_PAD, int SPL>
+__global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspace ws, RunParams rp, float *gamma,
+                                                               float *pi_io, const int32_t *__restrict__ n_states,
+                                                               double *Li, int32_t *n_iters, int32_t *flags,
+                                                               int iter) {
+    constexpr int LPR = S_PAD / SPL;
+    constexpr int RPW = 32 / LPR;
+    constexpr int PF = (SPL == 4) ? 8 : 12;  // prefetch distance (frames) of the forward sweep
+    constexpr int PB = (SPL == 4) ? 4 : 8;   // ... of the backward sweep (two arrays per frame)
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int g = lane / LPR, l = lane % LPR;
+    const int slot = warp_global * RPW + g;
+    int rec = -1;
+    if (slot < pl.n_rec) rec = pl.order[slot];
+    const bool live = rec >= 0 && ws.active[rec] != 0;
+    int64_t f0 = 0;
+    int T = 0;
+    if (live) {
+        f0 = pl.offsets[rec];
+        T = (int)(pl.offsets[rec + 1] - f0);
+    }
+    int Tmax = T;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, off));
+    if (Tmax == 0) return;  // warp-uniform
+    const int ns = live ? (n_states ? n_states[rec] : S_PAD) : 0;
+    const float P = rp.loopP, Q = 1.f - rp.loopP;
+
+    float pi[SPL], w[SPL], init[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int s = l * SPL + k;
+        const bool sl = live && s < ns;
+        pi[k] = sl ? pi_io[(int64_t)rec * S_PAD + s] : 0.f;
+        w[k] = sl ? fmaf(Q, pi[k], VBX_EPS_TR) : 0.f;   // VBx/VBx.py:98,159
+        init[k] = sl ? pi[k] + VBX_EPS_TR : 0.f;          // VBx/VBx.py:164
+    }
+    const float *pp = ws.p + f0 * S_PAD + l * SPL;
+    float *ga = gamma + f0 * S_PAD + l * SPL;
+    const float *mrow = ws.rowmax + f0;
+    float *rs = ws.rsigma + f0;
+
+    // ---------------- forward sweep, VBx/VBx.py:164,167-168,173 ----------------
+    float a[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) a[k] = 0.f;
+    double tll = 0.0;
+    {
+        Vec<SPL> pbuf[PF];
+        float mbuf[PF];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            if (i < T) {
+                pbuf[i] = ldg_vec<SPL>(pp + (int64_t)i * S_PAD);
+                mbuf[i] = __ldg(mrow + i);
+            } else {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) pbuf[i].v[k] = 0.f;
+                mbuf[i] = 0.f;
+            }
+        }
+        for (int t0 = 0; t0 < Tmax; t0 += PF) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                const int t = t0 + i;
+                const Vec<SPL> cur = pbuf[i];
+                const float cm = mbuf[i];
+                if (t + PF < T) {
+                    pbuf[i] = ldg_vec<SPL>(pp + (int64_t)(t + PF) * S_PAD);
+                    mbuf[i] = __ldg(mrow + t + PF);
+                }
+                float v[SPL], loc = 0.f;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    const float base = (t == 0) ? init[k] : fmaf(P, a[k], w[k]);
+                    v[k] = cur.v[k] * base;
+                    loc += v[k];
+                }
+                const float sig = group_sum<LPR>(loc);
+                if (t < T) {
+                    const float r = 1.f / sig;
+#pragma unroll
+                    for (int k = 0; k < SPL; ++k) a[k] = v[k] * r;
+                    st_vec<SPL>(ga + (int64_t)t * S_PAD, a);
+                    if (l == 0) rs[t] = r;
+                    tll += (double)(logf(sig) + cm);
+                }
+            }
+        }
+    }
+    __syncwarp();  // rsigma written by lane l==0 of each group is read by the whole group below
+
+    // ---------------- backward sweep, VBx/VBx.py:165,170-171,174 + eq. (24) statistics ----------------
+    float b[SPL], g0[SPL];
+    double enter[SPL], occ[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        b[k] = 1.f;
+        g0[k] = a[k];            // gamma_{T-1} = forward variable (already stored)
+        occ[k] = (double)a[k];
+        enter[k] = 0.0;
+    }
+    {
+        Vec<SPL> pb[PB], ab[PB];
+        float rb[PB];
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+            const int t = T - 2 - i;
+            if (t >= 0) {
+                pb[i] = ldg_vec<SPL>(pp + (int64_t)(t + 1) * S_PAD);
+                ab[i] = ld_vec<SPL>(ga + (int64_t)t * S_PAD);
+                rb[i] = rs[t + 1];
+            } else {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    pb[i].v[k] = 0.f;
+                    ab[i].v[k] = 0.f;
+                }
+                rb[i] = 0.f;
+            }
+        }
+        for (int i0 = 0; i0 < Tmax - 1; i0 += PB) {
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                const int t = T - 2 - (i0 + i);
+                const Vec<SPL> cp = pb[i], ca = ab[i];
+                const float cr = rb[i];
+                const int tn = t - PB;
+                if (tn >= 0) {
+                    pb[i] = ldg_vec<SPL>(pp + (int64_t)(tn + 1) * S_PAD);
+                    ab[i] = ld_vec<SPL>(ga + (int64_t)tn * S_PAD);
+                    rb[i] = rs[tn + 1];
+                }
+                float u[SPL], loc = 0.f;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    u[k] = (cp.v[k] * cr) * b[k];
+                    loc = fmaf(w[k], u[k], loc);
+                }
+                const float dot = group_sum<LPR>(loc);
+                if (t >= 0) {
+#pragma unroll
+                    for (int k = 0; k < SPL; ++k) {
+                        enter[k] += (double)u[k];
+                        b[k] = fmaf(P, u[k], dot);
+                        g0[k] = ca.v[k] * b[k];
+                        occ[k] += (double)g0[k];
+                    }
+                    st_vec<SPL>(ga + (int64_t)t * S_PAD, g0);
+                }
+            }
+        }
+    }
+
+    // ---------------- tail: eq. (24) VBx/VBx.py:101-104, eq. (25) :100,105, stop test :122-125 ----------------
+    double pn[SPL];
+    float loc = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        pn[k] = (double)g0[k] + (double)Q * (double)pi[k] * enter[k];
+        loc += (float)pn[k];
+    }
+    const float tot = group_sum<LPR>(loc);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int s = l * SPL + k;
+            pi_io[(int64_t)rec * S_PAD + s] = (float)(pn[k] / (double)tot);
+            ws.occ[(int64_t)rec * S_PAD + s] = (float)occ[k];
+        }
+        if (l == 0) {
+            const double elbo = tll + rp.dFa * ws.gsum[rec] + ws.reg[rec];
+            Li[(int64_t)rec * rp.max_iters + iter] = elbo;
+            n_iters[rec] = iter + 1;
+            int fl = flags[rec];
+            if (!isfinite(elbo)) fl |= 1;
+            if (iter > 0) {
+                const double d = elbo - ws.prev_elbo[rec];
+                if (d < rp.epsilon) {
+                    ws.active[rec] = 0;
+                    if (iter + 1 < rp.max_iters) fl |= 4;
+                    if (d < 0.0) fl |= 2;
+                }
+            }
+            ws.prev_elbo[rec] = elbo;
+            flags[rec] = fl;
+        }
+    }
+}
+
+template <int S_PAD, int SPL>
+static int launch_fb_t(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
+                       const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
+                       cudaStream_t st) {
+    constexpr int RPW = 32 / (S_PAD / SPL);
+    const int warps = (pl.n_rec + RPW - 1) / RPW;
+    const int blocks = (warps + 3) / 4;
+    forward_backward_kernel<S_PAD, SPL><<<blocks, 128, 0, st>>>(pl, ws, rp, gamma, pi, n_states, Li, n_iters, flags, iter);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
+                            const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
+                            int spl, cudaStream_t st) {
+    if (pl.n_rec == 0) return 0;
+#define VBX_FB(S_, L_) return launch_fb_t<S_, L_>(pl, ws, rp, gamma, pi, n_states, Li, n_iters, flags, iter, st)
+    const int S = pl.S;
+    if (spl == 0) spl = (S >= 64) ? 2 : (S >= 16 ? 2 : 1);
+    if (S == 64 && spl < 2) spl = 2;
+    if (spl > S) spl = S;
+    switch (S) {
+        case 4:
+            if (spl == 1) VBX_FB(4, 1);
+            if (spl == 2) VBX_FB(4, 2);
+            VBX_FB(4, 4);
+        case 8:
+            if (spl == 1) VBX_FB(8, 1);
+            if (spl == 2) VBX_FB(8, 2);
+            VBX_FB(8, 4);
+        case 16:
+            if (spl == 1) VBX_FB(16, 1);
+            if (spl == 2) VBX_FB(16, 2);
+            VBX_FB(16, 4);
+        case 32:
+            if (spl == 1) VBX_FB(32, 1);
+            if (spl == 2) VBX_FB(32, 2);
+            VBX_FB(32, 4);
+        case 64:
+            if (spl == 2) VBX_FB(64, 2);
+            VBX_FB(64, 4);
+        default: return -1;
+    }
+#undef VBX_FB
+}
+
+}  // namespace vbx
