@@ -59,7 +59,7 @@ int vbx_destroy(vbx_handle_t h);
 const char *vbx_last_error(vbx_handle_t h);
 
 /* Tuning knobs (ints): "fb_states_per_lane" (0 = auto, 1, 2, 4), "projection" (0 = auto, 1 = FFMA tiles,
- * 2 = tcgen05 3xTF32).  Unknown names return VBX_ERR_ARG. */
+ * 2 = tcgen05 3xTF32), "timing" (0/1, see vbx_get_timings).  Unknown names return VBX_ERR_ARG. */
 int vbx_set_option(vbx_handle_t h, const char *name, int32_t value);
 
 /* Describe a batch: offsets_host[n_rec+1] (HOST, int64, offsets_host[0] == 0), feature dim R
@@ -99,6 +99,22 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
 
 /* Number of kernels launched by this handle since creation (bench.py reports it as gpu_launches). */
 int64_t vbx_launch_count(vbx_handle_t h);
+
+/* Kernel classes for vbx_get_timings (measurement aid; no reference counterpart). */
+enum vbx_kernel_class {
+    VBX_K_PROJECT = 0,       /* rho = X.V                                   */
+    VBX_K_PREPARE = 1,       /* scale / G constant                          */
+    VBX_K_RUN_INIT = 2,
+    VBX_K_MSTEP = 3,         /* gamma^T rho tiles          VBx/VBx.py:96    */
+    VBX_K_SPEAKER_MODEL = 4, /* invL, alpha, bias, reg     VBx/VBx.py:95-96 */
+    VBX_K_LOGLIK = 5,        /* log_p_ + row softmax       VBx/VBx.py:97    */
+    VBX_K_FWDBWD = 6,        /* forward-backward, pi, ELBO VBx/VBx.py:98-105 */
+    VBX_N_KERNEL_CLASSES = 7
+};
+/* With option "timing" = 1 every kernel class is bracketed by CUDA events on the launching stream.
+ * Fills ms_out[VBX_N_KERNEL_CLASSES] / count_out[...] with the accumulated device time and launch counts
+ * (HOST arrays; synchronises on the recorded events); reset != 0 clears the accumulators. */
+int vbx_get_timings(vbx_handle_t h, double *ms_out, int64_t *count_out, int32_t reset);
 
 #ifdef __cplusplus
 }

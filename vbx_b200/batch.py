@@ -21,7 +21,7 @@ def _ptr(t):
 class VbxBatch:
     """Plan + workspace for one packed ragged batch on one device."""
 
-    def __init__(self, lengths, R, n_states, device=None):
+    def __init__(self, lengths, R, n_states, device=None, allocate=True):
         """lengths: per-recording frame counts T_b; R: feature dim seen by VBx() (VBx/VBx.py:74);
         n_states: int or per-recording ints (the `pi`-as-int / len(pi) of VBx/VBx.py:76-77)."""
         if not torch.cuda.is_available():
@@ -52,10 +52,16 @@ class VbxBatch:
                                       self.B, self.R, self.S, ctypes.byref(need)))
         self.workspace_bytes = int(need.value)
         with torch.cuda.device(self.device):
-            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
             self.n_states = None if self.uniform_states else torch.from_numpy(ns).to(self.device)
-        self._check(self.lib.vbx_bind_workspace(self._h, _ptr(self.workspace), self.workspace_bytes))
+        self.workspace = None
         self.rho = None
+        if allocate:
+            self.bind(torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device))
+
+    def bind(self, workspace):
+        """Attach a caller-owned uint8 CUDA tensor of at least `workspace_bytes` as the scratch space."""
+        self._check(self.lib.vbx_bind_workspace(self._h, _ptr(workspace), workspace.numel()))
+        self.workspace = workspace
 
     # ---- plumbing -------------------------------------------------------------------------
     def _check(self, rc):
@@ -81,10 +87,20 @@ class VbxBatch:
     def launches(self):
         return int(self.lib.vbx_launch_count(self._h))
 
+    def timings(self, reset=True):
+        """{kernel class: (total device ms, launches)} accumulated while option 'timing' was on."""
+        n = len(_lib.KERNEL_CLASSES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        self._check(self.lib.vbx_get_timings(self._h, ms, cnt, int(reset)))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _f32(self, t, shape, name):
+        if self.workspace is None:
+            raise VbxError('no workspace bound (VbxBatch(..., allocate=False) needs bind())')
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError(f'{name}: expected a contiguous float32 CUDA tensor')
         if tuple(t.shape) != tuple(shape):

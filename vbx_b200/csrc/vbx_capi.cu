@@ -19,7 +19,14 @@ struct vbx_handle_s {
     void *plan_mem = nullptr;  // one device allocation backing all plan arrays
     int opt_fb_spl = 0;
     int opt_projection = 0;
+    int opt_timing = 0;
     int64_t launches = 0;
+    // per-kernel-class CUDA-event timing (opt_timing): events are recorded on the launching stream
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<int> ev_class;  // class of the (2i, 2i+1) event pair
+    double t_ms[VBX_N_KERNEL_CLASSES] = {0};
+    int64_t t_cnt[VBX_N_KERNEL_CLASSES] = {0};
 };
 
 namespace {
@@ -95,10 +102,9 @@ int vbx_create(int32_t device, vbx_handle_t *out) {
 
 int vbx_destroy(vbx_handle_t h) {
     if (!h) return VBX_ERR_ARG;
-    if (h->plan_mem) {
-        cudaSetDevice(h->device);
-        cudaFree(h->plan_mem);
-    }
+    cudaSetDevice(h->device);
+    if (h->plan_mem) cudaFree(h->plan_mem);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return VBX_OK;
 }
@@ -110,6 +116,10 @@ int vbx_set_option(vbx_handle_t h, const char *name, int32_t value) {
     if (!strcmp(name, "fb_states_per_lane")) {
         if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, VBX_ERR_ARG, "fb_states_per_lane must be 0,1,2,4");
         h->opt_fb_spl = value;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "timing")) {
+        h->opt_timing = value ? 1 : 0;
         return VBX_OK;
     }
     if (!strcmp(name, "projection")) {
@@ -237,12 +247,36 @@ static int counted(vbx_handle_t h, int n, const char *what) {
     h->launches += n;
     return VBX_OK;
 }
+// Brackets one kernel class with a pair of events on `st` when timing is enabled.
+struct Timed {
+    vbx_handle_t h;
+    cudaStream_t st;
+    bool on;
+    Timed(vbx_handle_t h_, cudaStream_t st_, int cls) : h(h_), st(st_), on(h_->opt_timing != 0) {
+        if (!on) return;
+        while (h->ev_pool.size() < h->ev_used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+            h->ev_pool.push_back(e);
+        }
+        h->ev_class.push_back(cls);
+        cudaEventRecord(h->ev_pool[h->ev_used], st);
+    }
+    ~Timed() {
+        if (!on) return;
+        cudaEventRecord(h->ev_pool[h->ev_used + 1], st);
+        h->ev_used += 2;
+    }
+};
 
 int vbx_prepare_scale(vbx_handle_t h, const float *fea, const float *Phi, float *rho_out, void *stream) {
     int rc = check_ready(h, "vbx_prepare_scale");
     if (rc) return rc;
     if (h->plan.n_frames && (!fea || !Phi || !rho_out)) return fail(h, VBX_ERR_ARG, "vbx_prepare_scale: null pointer");
-    rc = counted(h, vbx::launch_prepare_scale(h->plan, h->ws, fea, Phi, rho_out, (cudaStream_t)stream), "prepare_scale");
+    {
+        Timed t(h, (cudaStream_t)stream, VBX_K_PREPARE);
+        rc = counted(h, vbx::launch_prepare_scale(h->plan, h->ws, fea, Phi, rho_out, (cudaStream_t)stream), "prepare_scale");
+    }
     if (rc) return rc;
     h->prepared = true;
     return VBX_OK;
@@ -256,6 +290,7 @@ int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *
     if (D < 32 || (D & 31)) return fail(h, VBX_ERR_ARG, "vbx_prepare_project: D must be a multiple of 32");
     cudaStream_t st = (cudaStream_t)stream;
     bool done = false;
+    Timed *tp = new Timed(h, st, VBX_K_PROJECT);
     if (h->opt_projection != 1) {
         std::string why;
         int n = vbx::launch_project_tcgen05(h->plan, X, D, V, rho_out, st, &why);
@@ -263,14 +298,17 @@ int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *
             h->launches += n;
             done = true;
         } else if (h->opt_projection == 2) {
+            delete tp;
             return fail(h, VBX_ERR_ARG, "vbx_prepare_project: tcgen05 path unavailable: " + why);
         }
     }
-    if (!done) {
-        rc = counted(h, vbx::launch_project_ffma(h->plan, X, D, V, rho_out, st), "project_ffma");
-        if (rc) return rc;
+    if (!done) rc = counted(h, vbx::launch_project_ffma(h->plan, X, D, V, rho_out, st), "project_ffma");
+    delete tp;
+    if (rc) return rc;
+    {
+        Timed t(h, st, VBX_K_PREPARE);
+        rc = counted(h, vbx::launch_g_from_rho(h->plan, h->ws, rho_out, Phi, st), "g_from_rho");
     }
-    rc = counted(h, vbx::launch_g_from_rho(h->plan, h->ws, rho_out, Phi, st), "g_from_rho");
     if (rc) return rc;
     h->prepared = true;
     return VBX_OK;
@@ -302,24 +340,63 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
     rp.loopP = (float)loop_prob;
     rp.max_iters = max_iters;
 
-    rc = counted(h, vbx::launch_run_init(pl, h->ws, gamma_io, n_states, Li_out, n_iters_out, flags_out, max_iters, st), "run_init");
+    {
+        Timed t(h, st, VBX_K_RUN_INIT);
+        rc = counted(h, vbx::launch_run_init(pl, h->ws, gamma_io, n_states, Li_out, n_iters_out, flags_out, max_iters, st), "run_init");
+    }
     if (rc) return rc;
     for (int it = 0; it < max_iters; ++it) {
         const bool given = it == 0 && warm_start;
         if (!given) {
+            Timed t(h, st, VBX_K_MSTEP);
             rc = counted(h, vbx::launch_mstep_partial(pl, h->ws, rho, gamma_io, st), "mstep_partial");
-            if (rc) return rc;
         }
-        rc = counted(h, vbx::launch_speaker_model(pl, h->ws, rp, Phi, n_states, alpha_io, invL_io, given, st), "speaker_model");
         if (rc) return rc;
-        rc = counted(h, vbx::launch_loglik(pl, h->ws, rho, st), "loglik");
+        {
+            Timed t(h, st, VBX_K_SPEAKER_MODEL);
+            rc = counted(h, vbx::launch_speaker_model(pl, h->ws, rp, Phi, n_states, alpha_io, invL_io, given, st), "speaker_model");
+        }
         if (rc) return rc;
-        rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, st), "forward_backward");
+        {
+            Timed t(h, st, VBX_K_LOGLIK);
+            rc = counted(h, vbx::launch_loglik(pl, h->ws, rho, st), "loglik");
+        }
+        if (rc) return rc;
+        {
+            Timed t(h, st, VBX_K_FWDBWD);
+            rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, st), "forward_backward");
+        }
         if (rc) return rc;
     }
     return VBX_OK;
 }
 
 int64_t vbx_launch_count(vbx_handle_t h) { return h ? h->launches : -1; }
+
+int vbx_get_timings(vbx_handle_t h, double *ms_out, int64_t *count_out, int32_t reset) {
+    if (!h) return VBX_ERR_ARG;
+    cudaSetDevice(h->device);
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        cudaError_t e = cudaEventSynchronize(h->ev_pool[i + 1]);
+        if (e != cudaSuccess) return cuda_fail(h, e, "cudaEventSynchronize");
+        float ms = 0.f;
+        e = cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]);
+        if (e != cudaSuccess) return cuda_fail(h, e, "cudaEventElapsedTime");
+        const int cls = h->ev_class[i / 2];
+        h->t_ms[cls] += ms;
+        h->t_cnt[cls] += 1;
+    }
+    h->ev_used = 0;
+    h->ev_class.clear();
+    for (int c = 0; c < VBX_N_KERNEL_CLASSES; ++c) {
+        if (ms_out) ms_out[c] = h->t_ms[c];
+        if (count_out) count_out[c] = h->t_cnt[c];
+        if (reset) {
+            h->t_ms[c] = 0.0;
+            h->t_cnt[c] = 0;
+        }
+    }
+    return VBX_OK;
+}
 
 }  // extern "C"
