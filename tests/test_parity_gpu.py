@@ -1,7 +1,9 @@
 """GPU parity: the CUDA path (through the C ABI) against the reference goldens and the CPU oracle.
 
 Tolerances (north_star: gamma/pi/Li within 1e-4 relative in float32):
-  gamma, pi : max|delta| <= 1e-4 * max|ref|      ELBO : |delta| <= 1e-4 * |ELBO|  (asserted at 1e-5)
+  gamma, pi : max|delta| <= 1e-4 * max|ref|      ELBO : |delta| <= 1e-4 * |ELBO| per iteration
+The ELBO of a *transient* iteration amplifies rounding differences (EM far from its fixed point), so on top of the
+official per-iteration bound the typical (median) relative ELBO error must be below 1e-6.
 """
 import os
 
@@ -14,7 +16,14 @@ from vbx_b200 import synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
-G_TOL, PI_TOL, L_RTOL = 1e-4, 1e-4, 1e-5
+G_TOL, PI_TOL, L_RTOL = 1e-4, 1e-4, 1e-4
+
+
+def check_elbo(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    np.testing.assert_allclose(got, want, rtol=L_RTOL)
+    rel = np.abs(got - want) / np.abs(want)
+    assert np.nanmedian(rel) < 1e-6, np.nanmedian(rel)
 
 
 def dev():
@@ -86,7 +95,7 @@ def test_reference_goldens(tag):
     assert n == len(c['Li']), (n, len(c['Li']))
     assert np.abs(out['gamma'] - c['gamma']).max() <= G_TOL * np.abs(c['gamma']).max()
     assert np.abs(out['pi'][0] - c['pi']).max() <= PI_TOL * np.abs(c['pi']).max()
-    np.testing.assert_allclose(out['Li'][0, :n], c['Li'], rtol=L_RTOL)
+    check_elbo(out['Li'][0, :n], c['Li'])
     assert np.all(np.isnan(out['Li'][0, n:]))
     assert np.abs(out['alpha'][0] - c['alpha']).max() <= 1e-4 * max(1.0, np.abs(c['alpha']).max())
     assert np.abs(out['invL'][0] - c['invL']).max() <= 1e-4
@@ -111,7 +120,7 @@ def test_es2005a_fixed_iterations():
                   loopProb=float(z['loopProb']), maxIters=13, epsilon=-np.inf)
     assert np.abs(out['gamma'] - z['gamma']).max() <= G_TOL
     assert np.abs(out['pi'][0] - z['pi']).max() <= PI_TOL
-    np.testing.assert_allclose(out['Li'][0], z['Li'], rtol=L_RTOL)
+    check_elbo(out['Li'][0], z['Li'])
     assert np.array_equal(out['gamma'].argmax(1), z['labels'])
 
 
@@ -155,7 +164,7 @@ def test_ragged_batch_vs_oracle(spl):
                   Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=8, epsilon=-np.inf)
     assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
     assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
-    np.testing.assert_allclose(out['Li'], ref['Li'], rtol=L_RTOL)
+    check_elbo(out['Li'], ref['Li'])
     assert np.all(out['n_iters'] == 8)
 
 
@@ -167,7 +176,7 @@ def test_state_counts_vs_oracle(S):
     out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=0.2, Fb=6.0, loopProb=0.35, maxIters=6, epsilon=-np.inf)
     assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
     assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
-    np.testing.assert_allclose(out['Li'], ref['Li'], rtol=L_RTOL)
+    check_elbo(out['Li'], ref['Li'])
 
 
 def test_small_feature_dims():
@@ -176,7 +185,7 @@ def test_small_feature_dims():
         ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(5, 0.2), 0.4, 17.0, 0.4, 5, -np.inf)
         out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=0.4, Fb=17.0, loopProb=0.4, maxIters=5, epsilon=-np.inf)
         assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
-        np.testing.assert_allclose(out['Li'], ref['Li'], rtol=L_RTOL)
+        check_elbo(out['Li'], ref['Li'])
 
 
 def test_per_recording_early_stop_in_a_batch():
@@ -192,7 +201,7 @@ def test_per_recording_early_stop_in_a_batch():
         lo, hi = d['offsets'][b], d['offsets'][b + 1]
         n = int(ref['n_iters'][b])
         assert np.abs(out['gamma'][lo:hi] - ref['gamma'][lo:hi]).max() <= G_TOL
-        np.testing.assert_allclose(out['Li'][b, :n], ref['Li'][b, :n], rtol=L_RTOL)
+        check_elbo(out['Li'][b, :n], ref['Li'][b, :n])
         assert np.all(np.isnan(out['Li'][b, n:]))
         assert bool(out['flags'][b] & 4) == (n < 30)
 
@@ -243,7 +252,7 @@ def test_full_pipeline_from_raw_xvectors():
     out = vb.run(g, p, Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=6, epsilon=-np.inf)
     torch.cuda.synchronize()
     assert np.abs(g.double().cpu().numpy() - ref['gamma']).max() <= G_TOL
-    np.testing.assert_allclose(out['Li'].cpu().numpy(), ref['Li'], rtol=L_RTOL)
+    check_elbo(out['Li'].cpu().numpy(), ref['Li'])
     vb.close()
 
 
@@ -271,7 +280,7 @@ def test_properties_at_scale():
     ref = co.vbx_oracle_batch(fea, d['Phi'], offs, g0, np.full(S, 1.0 / S), 0.3, 17.0, 0.99, 10, -np.inf)
     got = np.concatenate([out['gamma'][b * T:(b + 1) * T] for b in sel])
     assert np.abs(got - ref['gamma']).max() <= G_TOL
-    np.testing.assert_allclose(out['Li'][sel], ref['Li'], rtol=L_RTOL)
+    check_elbo(out['Li'][sel], ref['Li'])
 
 
 def test_dropin_vbx_function():
@@ -283,7 +292,7 @@ def test_dropin_vbx_function():
     assert g.dtype == np.float64 and p.dtype == np.float64 and isinstance(L, list) and isinstance(L[0], list)
     assert g.shape == c['gamma'].shape and p.shape == c['pi'].shape and len(L) == len(c['Li'])
     assert np.abs(g - c['gamma']).max() <= G_TOL
-    np.testing.assert_allclose([l[0] for l in L], c['Li'], rtol=L_RTOL)
+    check_elbo([l[0] for l in L], c['Li'])
     g2, p2, L2, a2, il2 = VBx(c['fea'], c['Phi'], loopProb=float(c['loopProb']), Fa=float(c['Fa']), Fb=float(c['Fb']),
                               pi=c['pi0'], gamma=c['gamma0'], maxIters=3, epsilon=-np.inf, return_model=True)
     assert a2.shape == c['alpha'].shape and il2.shape == c['invL'].shape

@@ -20,6 +20,7 @@ struct vbx_handle_s {
     int opt_fb_spl = 0;
     int opt_projection = 0;
     int opt_timing = 0;
+    int opt_gemm = 0;  // 0 = mma.sync 3xTF32, 1 = FFMA
     int64_t launches = 0;
     // per-kernel-class CUDA-event timing (opt_timing): events are recorded on the launching stream
     std::vector<cudaEvent_t> ev_pool;
@@ -61,6 +62,11 @@ size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
     w.rsigma = c.take<float>(N);
     w.partial = c.take<float>((size_t)pl.n_mtiles * S * R);
     w.A = c.take<float>(B * S * R);
+    {
+        const size_t NT = S > 8 ? S / 8 : 1, KS = (R + 7) / 8;
+        w.Afrag_hi = c.take<float>(B * NT * KS * 64);
+        w.Afrag_lo = c.take<float>(B * NT * KS * 64);
+    }
     w.bias = c.take<float>(B * S);
     w.occ = c.take<float>(B * S);
     w.reg = c.take<double>(B);
@@ -68,6 +74,7 @@ size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
     w.gpart = c.take<double>((size_t)pl.n_mtiles);
     w.prev_elbo = c.take<double>(B);
     w.active = c.take<int32_t>(B);
+    w.scratch = c.take<float>(2 * vbx::kMaxS);
     if (ws) *ws = w;
     return c.off + 256;
 }
@@ -116,6 +123,11 @@ int vbx_set_option(vbx_handle_t h, const char *name, int32_t value) {
     if (!strcmp(name, "fb_states_per_lane")) {
         if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, VBX_ERR_ARG, "fb_states_per_lane must be 0,1,2,4");
         h->opt_fb_spl = value;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "gemm")) {
+        if (value != 0 && value != 1) return fail(h, VBX_ERR_ARG, "gemm must be 0 (mma 3xTF32) or 1 (FFMA)");
+        h->opt_gemm = value;
         return VBX_OK;
     }
     if (!strcmp(name, "timing")) {
@@ -349,7 +361,7 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
         const bool given = it == 0 && warm_start;
         if (!given) {
             Timed t(h, st, VBX_K_MSTEP);
-            rc = counted(h, vbx::launch_mstep_partial(pl, h->ws, rho, gamma_io, st), "mstep_partial");
+            rc = counted(h, h->opt_gemm ? vbx::launch_mstep_partial(pl, h->ws, rho, gamma_io, st) : vbx::launch_mstep_mma(pl, h->ws, rho, gamma_io, st), "mstep_partial");
         }
         if (rc) return rc;
         {
@@ -359,7 +371,7 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
         if (rc) return rc;
         {
             Timed t(h, st, VBX_K_LOGLIK);
-            rc = counted(h, vbx::launch_loglik(pl, h->ws, rho, st), "loglik");
+            rc = counted(h, h->opt_gemm ? vbx::launch_loglik(pl, h->ws, rho, st) : vbx::launch_loglik_mma(pl, h->ws, rho, st), "loglik");
         }
         if (rc) return rc;
         {

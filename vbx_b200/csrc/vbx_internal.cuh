@@ -10,7 +10,7 @@
 namespace vbx {
 
 constexpr int kLTile = 64;    // frames per CTA tile of the log-likelihood kernel
-constexpr int kMTile = 256;   // frames per CTA tile of the M-step accumulation kernel
+constexpr int kMTile = 512;   // frames per CTA tile of the M-step accumulation / mma log-likelihood kernels
 constexpr int kMaxR = 128;
 constexpr int kMaxS = 64;
 
@@ -36,6 +36,8 @@ struct Workspace {
     float *rsigma = nullptr;   // [N]    1 / forward scale
     float *partial = nullptr;  // [n_mtiles,S,R] per-tile gamma^T rho
     float *A = nullptr;        // [n_rec,S,R]  Fa * alpha
+    float *Afrag_hi = nullptr; // [n_rec,NT,KS,32] float2: Fa*alpha split to TF32 hi/lo, mma fragment-major
+    float *Afrag_lo = nullptr; //   (NT = max(1,S/8) n-tiles, KS = ceil(R/8) k-steps; see vbx_mma_kernels.cu)
     float *bias = nullptr;     // [n_rec,S]    Fa * 0.5 * sum_r (invL + alpha^2) Phi_r ; +inf for dead columns
     float *occ = nullptr;      // [n_rec,S]    N_s = sum_t gamma
     double *reg = nullptr;     // [n_rec]      0.5 Fb sum (log invL - invL - alpha^2 + 1)
@@ -43,6 +45,7 @@ struct Workspace {
     double *gpart = nullptr;   // [n_mtiles]
     double *prev_elbo = nullptr; // [n_rec]
     int32_t *active = nullptr; // [n_rec]
+    float *scratch = nullptr;  // [2*kMaxS] write sink for warp lanes that own no recording
 };
 
 struct RunParams {
@@ -66,6 +69,9 @@ int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStr
 int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
                             int spl, cudaStream_t st);
+// tensor-core (mma.sync 3xTF32) versions of the two in-loop contractions (vbx_mma_kernels.cu)
+int launch_mstep_mma(const Plan &pl, const Workspace &ws, const float *rho, const float *gamma, cudaStream_t st);
+int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st);
 // tcgen05 projection (vbx_project_tc.cu)
 int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, float *rho, cudaStream_t st,
                            std::string *err);

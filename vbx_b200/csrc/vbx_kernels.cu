@@ -412,50 +412,71 @@ __global__ void __launch_bounds__(128) speaker_model_kernel(Plan pl, Workspace w
     const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
     const bool live = r < R;
     const int ns = n_states ? n_states[rec] : S;
-    const double phi = live ? (double)Phi[r] : 0.0;
+    const float phi = live ? Phi[r] : 0.f;
     const int t_lo = pl.mtile_begin[rec], t_hi = pl.mtile_begin[rec + 1];
-    __shared__ double sred[4];
+    __shared__ double cpart[4][kMaxS];
+    __shared__ double rpart[4];
+    // mma fragment-major copy of Fa*alpha, split into TF32 hi/lo (consumed by loglik_mma_kernel)
+    const int NT = S > 8 ? S / 8 : 1, KS = (R + 7) >> 3, KQ = 2 * KS;
+    const bool fragcol = r < 8 * KS;
+    // column r -> (k-step fj, quad lane fq, half fe); R = 128 uses the coalesced permutation of loglik_mma_kernel
+    const int fq = R == 128 ? (r >> 2) & 3 : r / KQ;
+    const int fj = R == 128 ? 2 * (r >> 4) + ((r >> 1) & 1) : (r - fq * KQ) >> 1;
+    const int fe = r & 1;
     double regacc = 0.0;
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < 8 * NT; ++s) {
         const int64_t o = ((int64_t)rec * S + s) * R + r;
-        if (s >= ns) {  // dead column: never wins, never contributes
-            if (live) {
+        const int64_t fo = (((int64_t)rec * NT + (s >> 3)) * KS + fj) * 64 + ((s & 7) * 4 + fq) * 2 + fe;
+        if (s >= ns) {  // dead (or padding) column: never wins, never contributes
+            if (live && s < S) {
                 ws.A[o] = 0.f;
                 if (alpha_io) alpha_io[o] = 0.f;
                 if (invL_io) invL_io[o] = 0.f;
             }
-            if (r == 0) ws.bias[(int64_t)rec * S + s] = CUDART_INF_F;
+            if (fragcol) {
+                ws.Afrag_hi[fo] = 0.f;
+                ws.Afrag_lo[fo] = 0.f;
+            }
             continue;
         }
-        double invL = 1.0, alpha = 0.0;
+        float invL = 1.f, alpha = 0.f, Av = 0.f;
+        double c = 0.0;
         if (live) {
             if (from_given) {
-                alpha = (double)alpha_io[o];
-                invL = (double)invL_io[o];
+                alpha = alpha_io[o];
+                invL = invL_io[o];
             } else {
                 double gr = 0.0;
                 for (int t = t_lo; t < t_hi; ++t) gr += (double)ws.partial[((int64_t)t * S + s) * R + r];
-                const double Ns = (double)ws.occ[(int64_t)rec * S + s];
-                invL = 1.0 / (1.0 + rp.dFaFb * Ns * phi);
-                alpha = rp.dFaFb * invL * gr;
-                if (alpha_io) alpha_io[o] = (float)alpha;
-                if (invL_io) invL_io[o] = (float)invL;
+                const float Ns = ws.occ[(int64_t)rec * S + s];
+                invL = 1.f / (1.f + rp.FaFb * Ns * phi);
+                alpha = (float)((double)(rp.FaFb * invL) * gr);
+                if (alpha_io) alpha_io[o] = alpha;
+                if (invL_io) invL_io[o] = invL;
             }
-            ws.A[o] = (float)(rp.dFa * alpha);
-            regacc += log(invL) - invL - alpha * alpha + 1.0;
+            Av = rp.Fa * alpha;
+            ws.A[o] = Av;
+            const float a2 = alpha * alpha;
+            regacc += (double)(logf(invL) - invL - a2 + 1.f);
+            c = (double)((invL + a2) * phi);
         }
-        double c = live ? (invL + alpha * alpha) * phi : 0.0;
+        if (fragcol) {
+            const float hi = __uint_as_float(__float_as_uint(Av) & 0xffffe000u);
+            ws.Afrag_hi[fo] = hi;
+            ws.Afrag_lo[fo] = Av - hi;
+        }
         c = warp_sum_d(c);
-        __syncthreads();
-        if (lane == 0) sred[warp] = c;
-        __syncthreads();
-        if (r == 0) ws.bias[(int64_t)rec * S + s] = (float)(rp.dFa * 0.5 * (sred[0] + sred[1] + sred[2] + sred[3]));
+        if (lane == 0) cpart[warp][s] = c;
     }
     regacc = warp_sum_d(regacc);
+    if (lane == 0) rpart[warp] = regacc;
     __syncthreads();
-    if (lane == 0) sred[warp] = regacc;
-    __syncthreads();
-    if (r == 0) ws.reg[rec] = 0.5 * rp.dFb * (sred[0] + sred[1] + sred[2] + sred[3]);
+    if (r < S) {
+        float bias = CUDART_INF_F;
+        if (r < ns) bias = (float)(rp.dFa * 0.5 * (cpart[0][r] + cpart[1][r] + cpart[2][r] + cpart[3][r]));
+        ws.bias[(int64_t)rec * S + r] = bias;
+    }
+    if (r == 0) ws.reg[rec] = 0.5 * rp.dFb * (rpart[0] + rpart[1] + rpart[2] + rpart[3]);
 }
 
 int launch_speaker_model(const Plan &pl, const Workspace &ws, const RunParams &rp, const float *Phi,
@@ -574,25 +595,35 @@ int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStr
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward-backward in the scaled linear domain                     VBx/VBx.py:98-105,122-125,146-175
+// forward-backward in the scaled linear domain                     VBx/VBx.py:98-104,146-175
 //
 // The transition matrix of VBx/VBx.py:98 is  loopP*I + (1-loopP)*1*pi^T ; with the reference's +1e-8
 // inside every log (VBx/VBx.py:159,164) it acts on a vector a as  loopP*a + w*sum(a),  w = (1-loopP)*pi + 1e-8,
 // so each frame costs O(S).  A group of LPR lanes owns one recording (SPL states per lane), 32/LPR
-// recordings share a warp.  Forward variables are normalised per frame (scale sigma_t); the backward
-// variables are scaled by the forward scales, so gamma_t = a_t * b_t sums to one without renormalising and
-// b_t stays within [1e-8, 1e8].  The same sweep accumulates N_s (VBx/VBx.py:95) and the re-entry statistics of
-// eq. (24) (VBx/VBx.py:101-103); the tail applies eq. (24)-(25) and the stop test (VBx/VBx.py:104-105,122-125).
+// recordings share a warp (recordings are sorted by length, so the groups of a warp finish together).
+// Forward variables are normalised per frame (scale sigma_t, its reciprocal is kept for the backward sweep and
+// for the ELBO kernel); the backward variables are scaled by the forward scales, so gamma_t = a_t * b_t sums to
+// one up to rounding and b_t stays within [1e-8, 1e8] (w >= 1e-8 bounds the spread of b_t).  The same sweep
+// accumulates N_s (VBx/VBx.py:95) and the re-entry statistics of eq. (24) (VBx/VBx.py:101-103); the tail applies
+// eq. (24) (VBx/VBx.py:101-104).
+//
+// Latency notes: every global load is an unconditional, index-clamped prefetch PF/PB frames ahead (a predicated
+// load turns into load+select and stalls on the spot); the main loops carry no per-group predicates, only the
+// ragged tail does; the reciprocal is a single MUFU.RCP.
 // ------------------------------------------------------------------------------------------------
-template <int S_PAD, int SPL>
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <int S_PAD, int SPL, bool NORM>
 __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspace ws, RunParams rp, float *gamma,
-                                                               float *pi_io, const int32_t *__restrict__ n_states,
-                                                               double *Li, int32_t *n_iters, int32_t *flags,
-                                                               int iter) {
+                                                               float *pi_io, const int32_t *__restrict__ n_states) {
     constexpr int LPR = S_PAD / SPL;
     constexpr int RPW = 32 / LPR;
-    constexpr int PF = (SPL == 4) ? 8 : 12;  // prefetch distance (frames) of the forward sweep
-    constexpr int PB = (SPL == 4) ? 4 : 8;   // ... of the backward sweep (two arrays per frame)
+    constexpr int PF = (SPL == 4) ? 8 : 16;  // frames per prefetch burst, forward sweep (ping-pong register sets)
+    constexpr int PB = (SPL == 4) ? 4 : 8;   // ... backward sweep (three arrays per frame)
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int g = lane / LPR, l = lane % LPR;
@@ -606,79 +637,96 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
         f0 = pl.offsets[rec];
         T = (int)(pl.offsets[rec + 1] - f0);
     }
-    int Tmax = T;
+    int Tmax = T, Tmin = live ? T : 0x7fffffff;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, off));
-    if (Tmax == 0) return;  // warp-uniform
+    for (int off = 16; off > 0; off >>= 1) {
+        Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, off));
+        Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, off));
+    }
+    if (Tmax == 0) return;  // warp-uniform: no live recording in this warp
+    const int Tlast = max(T - 1, 0);
     const int ns = live ? (n_states ? n_states[rec] : S_PAD) : 0;
     const float P = rp.loopP, Q = 1.f - rp.loopP;
 
-    float pi[SPL], w[SPL], init[SPL];
+    float pi[SPL], w[SPL], base[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         const int s = l * SPL + k;
         const bool sl = live && s < ns;
         pi[k] = sl ? pi_io[(int64_t)rec * S_PAD + s] : 0.f;
         w[k] = sl ? fmaf(Q, pi[k], VBX_EPS_TR) : 0.f;   // VBx/VBx.py:98,159
-        init[k] = sl ? pi[k] + VBX_EPS_TR : 0.f;          // VBx/VBx.py:164
+        base[k] = sl ? pi[k] + VBX_EPS_TR : 0.f;          // VBx/VBx.py:164 (initial state probabilities)
     }
+    // Groups without a recording read row 0 of the batch and write into a scratch row (stride 0), so that the
+    // main loops need no predicates at all.
     const float *pp = ws.p + f0 * S_PAD + l * SPL;
-    float *ga = gamma + f0 * S_PAD + l * SPL;
-    const float *mrow = ws.rowmax + f0;
-    float *rs = ws.rsigma + f0;
+    float *ga = live ? gamma + f0 * S_PAD + l * SPL : ws.scratch + l * SPL;
+    float *rs = live ? ws.rsigma + f0 : ws.scratch + kMaxS;
+    const int64_t gstr = live ? S_PAD : 0;
+    const int rstr = live ? 1 : 0;
 
-    // ---------------- forward sweep, VBx/VBx.py:164,167-168,173 ----------------
+    // ---------------- forward sweep, VBx/VBx.py:164,167-168 ----------------
     float a[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) a[k] = 0.f;
-    double tll = 0.0;
     {
-        Vec<SPL> pbuf[PF];
-        float mbuf[PF];
+        Vec<SPL> bufA[PF], bufB[PF];
+        auto fstep = [&](const int t, const Vec<SPL> &cur, const bool check) {
+            float v[SPL];
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            if (i < T) {
-                pbuf[i] = ldg_vec<SPL>(pp + (int64_t)i * S_PAD);
-                mbuf[i] = __ldg(mrow + i);
-            } else {
+            for (int k = 0; k < SPL; ++k) v[k] = cur.v[k] * base[k];
+            float loc = v[0];
 #pragma unroll
-                for (int k = 0; k < SPL; ++k) pbuf[i].v[k] = 0.f;
-                mbuf[i] = 0.f;
-            }
-        }
-        for (int t0 = 0; t0 < Tmax; t0 += PF) {
+            for (int k = 1; k < SPL; ++k) loc += v[k];
+            const float sig = group_sum<LPR>(loc);
+            const float r = rcp_fast(sig);
+            float an[SPL];
 #pragma unroll
-            for (int i = 0; i < PF; ++i) {
-                const int t = t0 + i;
-                const Vec<SPL> cur = pbuf[i];
-                const float cm = mbuf[i];
-                if (t + PF < T) {
-                    pbuf[i] = ldg_vec<SPL>(pp + (int64_t)(t + PF) * S_PAD);
-                    mbuf[i] = __ldg(mrow + t + PF);
-                }
-                float v[SPL], loc = 0.f;
+            for (int k = 0; k < SPL; ++k) an[k] = v[k] * r;
+            if (!check) {
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) {
-                    const float base = (t == 0) ? init[k] : fmaf(P, a[k], w[k]);
-                    v[k] = cur.v[k] * base;
-                    loc += v[k];
+                    a[k] = an[k];
+                    base[k] = fmaf(P, an[k], w[k]);
                 }
-                const float sig = group_sum<LPR>(loc);
-                if (t < T) {
-                    const float r = 1.f / sig;
+                st_vec<SPL>(ga + t * gstr, an);
+                if (l == 0) rs[t * rstr] = r;
+            } else {
+                const bool act = t < T;
 #pragma unroll
-                    for (int k = 0; k < SPL; ++k) a[k] = v[k] * r;
-                    st_vec<SPL>(ga + (int64_t)t * S_PAD, a);
-                    if (l == 0) rs[t] = r;
-                    tll += (double)(logf(sig) + cm);
+                for (int k = 0; k < SPL; ++k) {
+                    a[k] = act ? an[k] : a[k];
+                    base[k] = act ? fmaf(P, an[k], w[k]) : base[k];
+                }
+                if (act) {
+                    st_vec<SPL>(ga + t * gstr, an);
+                    if (l == 0) rs[t * rstr] = r;
                 }
             }
+        };
+        // one chunk = PF frames: first issue the burst of loads for the NEXT chunk, then run this chunk's steps
+        auto fchunk = [&](const int t0, Vec<SPL>(&cur)[PF], Vec<SPL>(&nxt)[PF], const bool check) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) nxt[i] = ldg_vec<SPL>(pp + (int64_t)min(t0 + PF + i, Tlast) * S_PAD);
+#pragma unroll
+            for (int i = 0; i < PF; ++i) fstep(t0 + i, cur[i], check);
+        };
+#pragma unroll
+        for (int i = 0; i < PF; ++i) bufA[i] = ldg_vec<SPL>(pp + (int64_t)min(i, Tlast) * S_PAD);
+        int t0 = 0;
+        for (; t0 + 2 * PF <= Tmin; t0 += 2 * PF) {
+            fchunk(t0, bufA, bufB, false);
+            fchunk(t0 + PF, bufB, bufA, false);
+        }
+        for (; t0 < Tmax; t0 += 2 * PF) {
+            fchunk(t0, bufA, bufB, true);
+            fchunk(t0 + PF, bufB, bufA, true);
         }
     }
     __syncwarp();  // rsigma written by lane l==0 of each group is read by the whole group below
 
     // ---------------- backward sweep, VBx/VBx.py:165,170-171,174 + eq. (24) statistics ----------------
-    float b[SPL], g0[SPL];
+    float b[SPL], g0[SPL], occf[SPL], entf[SPL];
     double enter[SPL], occ[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
@@ -686,60 +734,93 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
         g0[k] = a[k];            // gamma_{T-1} = forward variable (already stored)
         occ[k] = (double)a[k];
         enter[k] = 0.0;
+        occf[k] = 0.f;
+        entf[k] = 0.f;
     }
     {
-        Vec<SPL> pb[PB], ab[PB];
-        float rb[PB];
+        struct Slot {
+            Vec<SPL> p, a;
+            float r;
+        };
+        Slot bufA[PB], bufB[PB];
+        auto load_slot = [&](const int ii) {   // data of backward step ii (frame t = T-2-ii)
+            const int t = max(T - 2 - ii, 0);
+            const int t1 = min(t + 1, Tlast);
+            Slot sl;
+            sl.p = ldg_vec<SPL>(pp + (int64_t)t1 * S_PAD);
+            sl.a = ld_vec<SPL>(ga + t * gstr);
+            sl.r = rs[t1 * rstr];
+            return sl;
+        };
+        auto bstep = [&](const int ii, const Slot &c, const bool check) {
+            const int t = T - 2 - ii;
+            float u[SPL], loc = 0.f;
 #pragma unroll
-        for (int i = 0; i < PB; ++i) {
-            const int t = T - 2 - i;
-            if (t >= 0) {
-                pb[i] = ldg_vec<SPL>(pp + (int64_t)(t + 1) * S_PAD);
-                ab[i] = ld_vec<SPL>(ga + (int64_t)t * S_PAD);
-                rb[i] = rs[t + 1];
+            for (int k = 0; k < SPL; ++k) {
+                u[k] = (c.p.v[k] * c.r) * b[k];
+                loc = fmaf(w[k], u[k], loc);
+            }
+            const float dot = group_sum<LPR>(loc);
+            float gn[SPL], bn[SPL], gs = 0.f;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                bn[k] = fmaf(P, u[k], dot);
+                gn[k] = c.a.v[k] * bn[k];
+                gs += gn[k];
+            }
+            if (NORM) {  // remove the common-mode rounding drift: rows of gamma sum to one
+                const float sc = rcp_fast(group_sum<LPR>(gs));
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) gn[k] *= sc;
+            }
+            if (!check) {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    b[k] = bn[k];
+                    g0[k] = gn[k];
+                    occf[k] += gn[k];
+                    entf[k] += u[k];
+                }
+                st_vec<SPL>(ga + t * gstr, gn);
             } else {
+                const bool act = t >= 0;
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) {
-                    pb[i].v[k] = 0.f;
-                    ab[i].v[k] = 0.f;
+                    b[k] = act ? bn[k] : b[k];
+                    g0[k] = act ? gn[k] : g0[k];
+                    occf[k] += act ? gn[k] : 0.f;
+                    entf[k] += act ? u[k] : 0.f;
                 }
-                rb[i] = 0.f;
+                if (act) st_vec<SPL>(ga + t * gstr, gn);
             }
+        };
+        auto bchunk = [&](const int i0, Slot(&cur)[PB], Slot(&nxt)[PB], const bool check) {
+#pragma unroll
+            for (int i = 0; i < PB; ++i) nxt[i] = load_slot(i0 + PB + i);
+#pragma unroll
+            for (int i = 0; i < PB; ++i) bstep(i0 + i, cur[i], check);
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                occ[k] += (double)occf[k];
+                enter[k] += (double)entf[k];
+                occf[k] = 0.f;
+                entf[k] = 0.f;
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < PB; ++i) bufA[i] = load_slot(i);
+        int i0 = 0;
+        for (; i0 + 2 * PB <= Tmin - 1; i0 += 2 * PB) {
+            bchunk(i0, bufA, bufB, false);
+            bchunk(i0 + PB, bufB, bufA, false);
         }
-        for (int i0 = 0; i0 < Tmax - 1; i0 += PB) {
-#pragma unroll
-            for (int i = 0; i < PB; ++i) {
-                const int t = T - 2 - (i0 + i);
-                const Vec<SPL> cp = pb[i], ca = ab[i];
-                const float cr = rb[i];
-                const int tn = t - PB;
-                if (tn >= 0) {
-                    pb[i] = ldg_vec<SPL>(pp + (int64_t)(tn + 1) * S_PAD);
-                    ab[i] = ld_vec<SPL>(ga + (int64_t)tn * S_PAD);
-                    rb[i] = rs[tn + 1];
-                }
-                float u[SPL], loc = 0.f;
-#pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    u[k] = (cp.v[k] * cr) * b[k];
-                    loc = fmaf(w[k], u[k], loc);
-                }
-                const float dot = group_sum<LPR>(loc);
-                if (t >= 0) {
-#pragma unroll
-                    for (int k = 0; k < SPL; ++k) {
-                        enter[k] += (double)u[k];
-                        b[k] = fmaf(P, u[k], dot);
-                        g0[k] = ca.v[k] * b[k];
-                        occ[k] += (double)g0[k];
-                    }
-                    st_vec<SPL>(ga + (int64_t)t * S_PAD, g0);
-                }
-            }
+        for (; i0 < Tmax - 1; i0 += 2 * PB) {
+            bchunk(i0, bufA, bufB, true);
+            bchunk(i0 + PB, bufB, bufA, true);
         }
     }
 
-    // ---------------- tail: eq. (24) VBx/VBx.py:101-104, eq. (25) :100,105, stop test :122-125 ----------------
+    // ---------------- tail: eq. (24), VBx/VBx.py:101-104 ----------------
     double pn[SPL];
     float loc = 0.f;
 #pragma unroll
@@ -755,69 +836,96 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
             pi_io[(int64_t)rec * S_PAD + s] = (float)(pn[k] / (double)tot);
             ws.occ[(int64_t)rec * S_PAD + s] = (float)occ[k];
         }
-        if (l == 0) {
-            const double elbo = tll + rp.dFa * ws.gsum[rec] + ws.reg[rec];
-            Li[(int64_t)rec * rp.max_iters + iter] = elbo;
-            n_iters[rec] = iter + 1;
-            int fl = flags[rec];
-            if (!isfinite(elbo)) fl |= 1;
-            if (iter > 0) {
-                const double d = elbo - ws.prev_elbo[rec];
-                if (d < rp.epsilon) {
-                    ws.active[rec] = 0;
-                    if (iter + 1 < rp.max_iters) fl |= 4;
-                    if (d < 0.0) fl |= 2;
-                }
-            }
-            ws.prev_elbo[rec] = elbo;
-            flags[rec] = fl;
-        }
     }
 }
 
 template <int S_PAD, int SPL>
 static int launch_fb_t(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
-                       const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
-                       cudaStream_t st) {
+                       const int32_t *n_states, cudaStream_t st) {
     constexpr int RPW = 32 / (S_PAD / SPL);
     const int warps = (pl.n_rec + RPW - 1) / RPW;
     const int blocks = (warps + 3) / 4;
-    forward_backward_kernel<S_PAD, SPL><<<blocks, 128, 0, st>>>(pl, ws, rp, gamma, pi, n_states, Li, n_iters, flags, iter);
+    forward_backward_kernel<S_PAD, SPL, true><<<blocks, 128, 0, st>>>(pl, ws, rp, gamma, pi, n_states);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ELBO + stop test: one warp per recording                         VBx/VBx.py:100,105,122-125,173
+//   tll = sum_t (log sigma_t + rowmax_t) + Fa * sum_t G_t ;  ELBO = tll + reg
+// float64, fixed summation order (lane-strided partial sums, xor tree) => deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) elbo_kernel(Plan pl, Workspace ws, RunParams rp, double *Li, int32_t *n_iters,
+                                                   int32_t *flags, int iter) {
+    const int rec = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (rec >= pl.n_rec || !ws.active[rec]) return;
+    const int64_t f0 = pl.offsets[rec];
+    const int T = (int)(pl.offsets[rec + 1] - f0);
+    const float *rs = ws.rsigma + f0;
+    const float *mx = ws.rowmax + f0;
+    double acc = 0.0;
+    for (int t = lane; t < T; t += 32) acc += (double)mx[t] - log((double)rs[t]);
+    acc = warp_sum_d(acc);
+    if (lane == 0) {
+        const double elbo = acc + rp.dFa * ws.gsum[rec] + ws.reg[rec];
+        Li[(int64_t)rec * rp.max_iters + iter] = elbo;
+        n_iters[rec] = iter + 1;
+        int fl = flags[rec];
+        if (!isfinite(elbo)) fl |= 1;
+        if (iter > 0) {
+            const double d = elbo - ws.prev_elbo[rec];
+            if (d < rp.epsilon) {  // VBx/VBx.py:122: stop AFTER this iteration's update
+                ws.active[rec] = 0;
+                if (iter + 1 < rp.max_iters) fl |= 4;
+                if (d < 0.0) fl |= 2;
+            }
+        }
+        ws.prev_elbo[rec] = elbo;
+        flags[rec] = fl;
+    }
 }
 
 int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
                             int spl, cudaStream_t st) {
     if (pl.n_rec == 0) return 0;
-#define VBX_FB(S_, L_) return launch_fb_t<S_, L_>(pl, ws, rp, gamma, pi, n_states, Li, n_iters, flags, iter, st)
+    int rc = -1;
+#define VBX_FB(S_, L_) rc = launch_fb_t<S_, L_>(pl, ws, rp, gamma, pi, n_states, st)
     const int S = pl.S;
-    if (spl == 0) spl = (S >= 64) ? 2 : (S >= 16 ? 2 : 1);
+    if (spl == 0) spl = (S >= 16) ? 2 : 1;
     if (S == 64 && spl < 2) spl = 2;
     if (spl > S) spl = S;
     switch (S) {
         case 4:
             if (spl == 1) VBX_FB(4, 1);
-            if (spl == 2) VBX_FB(4, 2);
-            VBX_FB(4, 4);
+            else if (spl == 2) VBX_FB(4, 2);
+            else VBX_FB(4, 4);
+            break;
         case 8:
             if (spl == 1) VBX_FB(8, 1);
-            if (spl == 2) VBX_FB(8, 2);
-            VBX_FB(8, 4);
+            else if (spl == 2) VBX_FB(8, 2);
+            else VBX_FB(8, 4);
+            break;
         case 16:
             if (spl == 1) VBX_FB(16, 1);
-            if (spl == 2) VBX_FB(16, 2);
-            VBX_FB(16, 4);
+            else if (spl == 2) VBX_FB(16, 2);
+            else VBX_FB(16, 4);
+            break;
         case 32:
             if (spl == 1) VBX_FB(32, 1);
-            if (spl == 2) VBX_FB(32, 2);
-            VBX_FB(32, 4);
+            else if (spl == 2) VBX_FB(32, 2);
+            else VBX_FB(32, 4);
+            break;
         case 64:
             if (spl == 2) VBX_FB(64, 2);
-            VBX_FB(64, 4);
+            else VBX_FB(64, 4);
+            break;
         default: return -1;
     }
 #undef VBX_FB
+    if (rc < 0) return rc;
+    elbo_kernel<<<(pl.n_rec + 3) / 4, 128, 0, st>>>(pl, ws, rp, Li, n_iters, flags, iter);
+    return cudaGetLastError() == cudaSuccess ? rc + 1 : -1;
 }
 
 }  // namespace vbx
