@@ -237,6 +237,32 @@ def test_projection_matches_fp32_matmul():
     vb.close()
 
 
+@pytest.mark.parametrize('n_rec,T', [(4, 119), (300, 1000)])
+def test_projection_tcgen05(n_rec, T):
+    """The tcgen05/TMEM 3xTF32 projection kernel against a float64 matmul (several tiles per persistent CTA)."""
+    from vbx_b200.batch import VbxBatch
+    lens = [T] * n_rec
+    rng = np.random.default_rng(7)
+    N = n_rec * T
+    X = rng.standard_normal((N, 256)).astype(np.float32) * 3.0
+    V = (synth.projection_basis(256, 128) * np.sqrt(synth.plda_phi(128))[None, :]).astype(np.float32)
+    vb = VbxBatch(lens, 128, 4, device=dev())
+    vb.set_option('projection', 2)
+    rho = vb.prepare_project(cuda(X), cuda(V), cuda(synth.plda_phi(128)))
+    torch.cuda.synchronize()
+    got = rho.double().cpu().numpy()
+    want = X.astype(np.float64) @ V.astype(np.float64)
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err <= 5e-6, err
+    vb.set_option('projection', 1)
+    rho2 = vb.prepare_project(cuda(X), cuda(V), cuda(synth.plda_phi(128)))
+    torch.cuda.synchronize()
+    err2 = np.abs(rho2.double().cpu().numpy() - want).max() / np.abs(want).max()
+    print("projection error: tcgen05 3xTF32 %.2e, FFMA %.2e" % (err, err2))
+    assert err <= 32 * err2 + 1e-7, (err, err2)       # split-precision tensor cores stay near FFMA-level accuracy
+    vb.close()
+
+
 def test_full_pipeline_from_raw_xvectors():
     """X (D=256) -> rho = X.V -> EM: equals the oracle run on fea = X.V0."""
     from vbx_b200.batch import VbxBatch

@@ -303,7 +303,7 @@ int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *
     cudaStream_t st = (cudaStream_t)stream;
     bool done = false;
     Timed *tp = new Timed(h, st, VBX_K_PROJECT);
-    if (h->opt_projection != 1) {
+    if (h->opt_projection != 1) {   // auto: tcgen05 when the shape allows it (R == 128, D % 32 == 0), else FFMA tiles
         std::string why;
         int n = vbx::launch_project_tcgen05(h->plan, X, D, V, rho_out, st, &why);
         if (n >= 0) {

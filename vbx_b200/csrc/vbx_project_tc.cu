@@ -1,10 +1,362 @@
-// tcgen05 (5th-gen tensor core) projection rho = X . V with 3xTF32 split precision.
-// Placeholder until the UMMA/TMA kernel lands: reports "unavailable" so the C ABI uses the FFMA tiles.
+// Projection  rho[N,128] = X[N,D] . V[D,128]  on the 5th-generation tensor cores (tcgen05 / UMMA, sm_100a),
+// in split-precision 3xTF32 (x_lo*v_hi + x_hi*v_lo + x_hi*v_hi, fp32 accumulation in TMEM) because plain TF32
+// breaks the 1e-4 parity bar of the EM loop (hard part 4).
+// Reference: the caller-side projection VBx/vbhmm.py:129,153 folded with the scale VBx/VBx.py:88-89.
+//
+// One persistent CTA per SM, 13 warps:
+//   warps 0-7  producers: coalesced LDG of a 256-frame x 32-column block of X (prefetched one block ahead in
+//              registers), split into TF32 hi/lo, stored into the 128B-swizzled K-major UMMA layout;
+//              thread 0 also issues the bulk-async (TMA, cp.async.bulk) copies of the pre-split V block.
+//   warp  8    MMA issuer: one thread issues 24 tcgen05.mma (M128 x N128 x K8, kind::tf32) per 32-column block
+//              (2 M-tiles x 4 k-steps x 3 split terms); tcgen05.commit releases the smem stage / publishes the
+//              accumulator.
+//   warps 9-12 epilogue: tcgen05.ld the 2 x (128 x 128) fp32 accumulators out of TMEM and store rho.
+// Shared memory: 2 stages x (A hi/lo for 2 M-tiles 64 KB + B hi/lo 32 KB) = 192 KB.  TMEM: 2 accumulator sets of
+// 256 columns (all 512), so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
 #include "vbx_internal.cuh"
 
 namespace vbx {
-int launch_project_tcgen05(const Plan &, const float *, int, const float *, float *, cudaStream_t, std::string *err) {
-    if (err) *err = "not built";
-    return -1;
+
+namespace {
+
+constexpr int kTileM = 256;                 // frames per CTA tile (two UMMA M=128 tiles)
+constexpr int kKB = 32;                     // columns of X per pipeline block (= one 128-byte swizzle row)
+constexpr int kStages = 2;
+constexpr int kABytes = 128 * 128;          // one 128-row x 128-byte operand image
+constexpr int kStageBytes = 4 * kABytes + 2 * kABytes;  // A: 2 mtiles x hi/lo, B: hi/lo
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = 13 * 32;
+constexpr uint32_t kTmemCols = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both K-major, kind::tf32
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle, dense 8-row groups (SBO = 1024 B), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+    d |= (uint64_t)1 << 46;                            // version
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void split_rn(const float x, float &hi, float &lo) {
+    const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    hi = __uint_as_float(h);
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
+
+// ---- setup: V [D,128] -> per 32-row block of V the swizzled K-major images of V^T, hi and lo (16 KB each) ----
+__global__ void build_v_images_kernel(const float *__restrict__ V, int D, float *__restrict__ img) {
+    const int kb = blockIdx.x;                       // k-block
+    for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) {
+        const int n = i >> 5, kk = i & 31;           // row n of V^T, column kk inside the block
+        const float v = V[(int64_t)(kb * kKB + kk) * 128 + n];
+        float hi, lo;
+        split_rn(v, hi, lo);
+        const int c = kk >> 2, e = kk & 3;
+        const int off = n * 32 + (((c ^ (n & 7)) << 2) | e);   // float index inside the 16 KB image
+        img[(int64_t)kb * 2 * 4096 + off] = hi;
+        img[(int64_t)kb * 2 * 4096 + 4096 + off] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vimg, float *__restrict__ rho, int64_t N,
+                       int D) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned stage buffers (required by the 128-byte swizzle)
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    // barrier ids
+    auto full_a = [&](int s) { return bar_base + 8u * (0 + s); };
+    auto full_b = [&](int s) { return bar_base + 8u * (2 + s); };
+    auto empty = [&](int s) { return bar_base + 8u * (4 + s); };
+    auto tmem_full = [&](int a) { return bar_base + 8u * (6 + a); };
+    auto tmem_empty = [&](int a) { return bar_base + 8u * (8 + a); };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_kb = D / kKB;
+    const int64_t n_tiles = (N + kTileM - 1) / kTileM;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_a(s), kProducerThreads);
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ======================= producers =======================
+        const int c = tid & 7;            // 16-byte chunk inside the 128-byte row
+        const int r0 = tid >> 3;          // rows r0 + 32 i, i = 0..7
+        float4 cur[8], nxt[8];
+        auto load_block = [&](int64_t tile, int kb, float4(&buf)[8]) {
+            const int64_t row_base = tile * kTileM;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t row = min(row_base + r0 + 32 * i, N - 1);
+                buf[i] = __ldg(reinterpret_cast<const float4 *>(X + row * D + kb * kKB) + c);
+            }
+        };
+        int64_t tile = blockIdx.x;
+        int kb = 0;
+        if (tile < n_tiles) load_block(tile, 0, cur);
+        int s = 0;
+        uint32_t ph = 0;
+        while (tile < n_tiles) {
+            // prefetch the next block of X while this one is split and stored
+            int64_t ntile = tile;
+            int nkb = kb + 1;
+            if (nkb == n_kb) {
+                nkb = 0;
+                ntile = tile + gridDim.x;
+            }
+            if (ntile < n_tiles) load_block(ntile, nkb, nxt);
+            mbar_wait(empty(s), ph ^ 1);               // the MMAs that read this stage have completed
+            uint8_t *stage = smem + s * kStageBytes;
+            if (tid == 0) {
+                mbar_expect_tx(full_b(s), 2 * kABytes);
+                bulk_g2s(smem_u32(stage + 4 * kABytes), vimg + (int64_t)kb * 2 * 4096, 2 * kABytes, full_b(s));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 32 * i;             // 0..255
+                const int mt = r >> 7, m = r & 127;
+                float4 hi, lo;
+                split_rn(cur[i].x, hi.x, lo.x);
+                split_rn(cur[i].y, hi.y, lo.y);
+                split_rn(cur[i].z, hi.z, lo.z);
+                split_rn(cur[i].w, hi.w, lo.w);
+                const int off = m * 128 + ((c ^ (m & 7)) << 4);
+                *reinterpret_cast<float4 *>(stage + (mt * 2 + 0) * kABytes + off) = hi;
+                *reinterpret_cast<float4 *>(stage + (mt * 2 + 1) * kABytes + off) = lo;
+            }
+            fence_proxy_async_smem();                  // make the generic-proxy stores visible to the tensor core
+            mbar_arrive(full_a(s));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            tile = ntile;
+            kb = nkb;
+            if (++s == kStages) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    } else if (warp == 8) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t acc_ph = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(tmem_empty(acc), acc_ph ^ 1);   // epilogue has drained this accumulator set
+                tc_fence_after();
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(full_a(s), ph);
+                    mbar_wait(full_b(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * kStageBytes;
+                    const uint32_t b_hi = st + 4 * kABytes, b_lo = b_hi + kABytes;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint32_t a_hi = st + (mt * 2 + 0) * kABytes, a_lo = a_hi + kABytes;
+                        const uint32_t d = tmem_base + (uint32_t)(acc * 256 + mt * 128);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t koff = ks * 32;     // 8 tf32 = 32 bytes inside the swizzle row
+                            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                            umma_tf32(d, make_desc(a_lo + koff), make_desc(b_hi + koff), kIdesc, first);
+                            umma_tf32(d, make_desc(a_hi + koff), make_desc(b_lo + koff), kIdesc, 1u);
+                            umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + koff), kIdesc, 1u);
+                        }
+                    }
+                    tc_commit(empty(s));                       // stage reusable once these MMAs retire
+                    if (kb == n_kb - 1) tc_commit(tmem_full(acc));
+                    if (++s == kStages) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_ph ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ======================= epilogue =======================
+        const int quarter = warp & 3;                  // TMEM lanes 32*quarter .. +31 are visible to this warp
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(tmem_full(acc), acc_ph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < 2; ++mt) {
+                const int64_t row = tile * kTileM + mt * 128 + quarter * 32 + lane;
+                float *dst = rho + row * 128;
+#pragma unroll 1
+                for (int cb = 0; cb < 4; ++cb) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + mt * 128 + cb * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row < N) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<uint4 *>(dst + cb * 32 + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_ph ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+struct TcState {
+    float *vimg = nullptr;
+    size_t vimg_bytes = 0;
+    int device = -1;
+    bool configured = false;
+};
+TcState g_tc[16];
+
+}  // namespace
+
+int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, float *rho, cudaStream_t st,
+                           std::string *err) {
+    if (pl.R != 128) {
+        if (err) *err = "tcgen05 projection needs R == 128";
+        return -1;
+    }
+    if (D % kKB != 0 || D < kKB) {
+        if (err) *err = "tcgen05 projection needs D to be a multiple of 32";
+        return -1;
+    }
+    if (pl.n_frames == 0) return 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) {
+        if (err) *err = "device index out of range";
+        return -1;
+    }
+    TcState &tc = g_tc[dev];
+    const size_t need = (size_t)(D / kKB) * 2 * kABytes;
+    if (tc.vimg_bytes < need) {
+        if (tc.vimg) cudaFree(tc.vimg);
+        tc.vimg = nullptr;
+        if (cudaMalloc(&tc.vimg, need) != cudaSuccess) {
+            if (err) *err = "cudaMalloc(V images) failed";
+            tc.vimg_bytes = 0;
+            return -1;
+        }
+        tc.vimg_bytes = need;
+    }
+    const int smem = kStages * kStageBytes + 1024 + 256;
+    if (!tc.configured) {
+        if (cudaFuncSetAttribute(project_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            if (err) *err = "cudaFuncSetAttribute(smem) failed";
+            return -1;
+        }
+        tc.configured = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    build_v_images_kernel<<<D / kKB, 256, 0, st>>>(V, D, tc.vimg);
+    const int64_t n_tiles = (pl.n_frames + kTileM - 1) / kTileM;
+    const int grid = (int)std::min<int64_t>(n_tiles, sms);
+    project_tcgen05_kernel<<<grid, kThreads, smem, st>>>(X, tc.vimg, rho, pl.n_frames, D);
+    if (cudaGetLastError() != cudaSuccess) {
+        if (err) *err = "tcgen05 projection launch failed";
+        return -1;
+    }
+    return 2;
+}
+
 }  // namespace vbx
