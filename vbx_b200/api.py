@@ -50,7 +50,8 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
     if dev is None:
         raise _lib.VbxError('VBx(): no CUDA device - vbx_b200 has no CPU fallback')
     vb = VbxBatch([T], D, S, device=dev)
-    Sp = vb.S
+    vb.set_option('gemm', 1)      # single recording: float32 FFMA contractions (closest to the float64 reference);
+    Sp = vb.S                     # the batched API defaults to tensor cores in split-precision 3xTF32
     fea_d = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(dev)
     phi_d = torch.from_numpy(np.ascontiguousarray(Phi, dtype=np.float32)).to(dev)
     g = torch.zeros((T, Sp), dtype=torch.float32, device=dev)

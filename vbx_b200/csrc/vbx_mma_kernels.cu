@@ -15,6 +15,10 @@
 
 #include "vbx_internal.cuh"
 
+#ifndef VBX_L2_PREFETCH
+#define VBX_L2_PREFETCH 0
+#endif
+
 namespace vbx {
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
@@ -32,6 +36,11 @@ __device__ __forceinline__ void split_tf32(const float x, uint32_t &hi, uint32_t
     asm volatile("{\n\t.reg .b32 t;\n\tadd.u32 t, %1, 0x1000;\n\tand.b32 %0, t, 0xffffe000;\n\t}" : "=r"(hi) : "r"(__float_as_uint(x)));
     lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
 }
+// Bulk L2 prefetch (one instruction for a contiguous block): pulls future rows of rho from HBM into L2 so that the
+// register-staged fragment loads see L2 latency instead of DRAM latency, without holding registers for them.
+__device__ __forceinline__ void prefetch_l2(const void *gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async16_(void *smem, const void *gmem) {
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -45,7 +54,7 @@ __device__ __forceinline__ void cp_async16_(void *smem, const void *gmem) {
 // the slots are summed through shared memory in fixed order (deterministic).
 // ------------------------------------------------------------------------------------------------
 template <int S_PAD>
-__global__ void __launch_bounds__(128, 2) mstep_mma_kernel(Plan pl, Workspace ws, const float *__restrict__ rho,
+__global__ void __launch_bounds__(128, 4) mstep_mma_kernel(Plan pl, Workspace ws, const float *__restrict__ rho,
                                                            const float *__restrict__ gamma) {
     constexpr int MT = S_PAD > 16 ? S_PAD / 16 : 1;  // m-tiles of 16 states
     constexpr int NTW = 16 / MT;                     // n-tiles (8 r each) per warp
@@ -131,14 +140,20 @@ __global__ void __launch_bounds__(128, 2) mstep_mma_kernel(Plan pl, Workspace ws
         }
     };
     const int nchunks = (len + 7) >> 3;
+    constexpr int PD = 8;  // L2 prefetch distance in chunks of this warp's slot (8 frames x R floats each)
+    auto prefetch_chunk = [&](const int c) {
+        if (VBX_L2_PREFETCH && lane == 0 && rg == 0 && 8 * c + 8 <= len) prefetch_l2(rho + (f0 + 8 * c) * R, 8 * R * 4);
+    };
     {
-        Raw ra, rb;
-        load_chunk(fs, ra);
-        for (int c = fs; c < nchunks; c += 2 * FS) {
-            load_chunk(c + FS, rb);
+        // Latency is covered by (a) the bulk L2 prefetch PD chunks ahead and (b) 16 resident warps per SM; the
+        // fragment registers are single-buffered to keep the kernel at <= 128 registers (4 CTAs per SM).
+#pragma unroll
+        for (int k = 1; k < PD; ++k) prefetch_chunk(fs + k * FS);
+        Raw ra;
+        for (int c = fs; c < nchunks; c += FS) {
+            prefetch_chunk(c + PD * FS);
+            load_chunk(c, ra);
             compute(ra, c);
-            load_chunk(c + 2 * FS, ra);
-            if (c + FS < nchunks) compute(rb, c + FS);
         }
     }
     // every slot parks its fragment in shared memory, then the CTA sums the slots in fixed order
@@ -193,7 +208,7 @@ int launch_mstep_mma(const Plan &pl, const Workspace &ws, const float *rho, cons
 // One CTA (4 warps) per <=256-frame tile, a warp owns every 4th 16-frame m-tile.
 // ------------------------------------------------------------------------------------------------
 template <int S_PAD, bool R128>
-__global__ void __launch_bounds__(128, 2) loglik_mma_kernel(Plan pl, Workspace ws,
+__global__ void __launch_bounds__(128, 3) loglik_mma_kernel(Plan pl, Workspace ws,
                                                                                const float *__restrict__ rho) {
     constexpr int NT = S_PAD > 8 ? S_PAD / 8 : 1;
     extern __shared__ uint2 sfrag[];
@@ -227,7 +242,11 @@ __global__ void __launch_bounds__(128, 2) loglik_mma_kernel(Plan pl, Workspace w
     }
     const int n_mt = (len + 15) >> 4;
 
-    auto finish = [&](float (&D)[NT][4], const int mt) {
+    auto finish = [&](float (&D)[NT][4], const float (&E)[NT][4], const int mt) {
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) D[i][e] += E[i][e];
         float m0 = fmaxf(D[0][0], D[0][1]), m1 = fmaxf(D[0][2], D[0][3]);
 #pragma unroll
         for (int i = 1; i < NT; ++i) {
@@ -254,7 +273,10 @@ __global__ void __launch_bounds__(128, 2) loglik_mma_kernel(Plan pl, Workspace w
             if (rb < len) ws.rowmax[f0 + rb] = m1;
         }
     };
-    auto kstep = [&](float (&D)[NT][4], const int j, const float a0, const float a1, const float a2, const float a3) {
+    // The split terms go to separate accumulators (E: lo*hi + hi*lo, D: hi*hi) so that consecutive mma of a k-step
+    // do not depend on each other; E is folded into D in finish().
+    auto kstep = [&](float (&D)[NT][4], float (&E)[NT][4], const int j, const float a0, const float a1, const float a2,
+                     const float a3) {
         uint32_t ah[4], al[4];
         split_tf32(a0, ah[0], al[0]);
         split_tf32(a1, ah[1], al[1]);
@@ -264,9 +286,9 @@ __global__ void __launch_bounds__(128, 2) loglik_mma_kernel(Plan pl, Workspace w
         for (int i = 0; i < NT; ++i) {
             const uint2 bh = sBh[(i * KS + j) * 32 + lane];
             const uint2 bl = sBl[(i * KS + j) * 32 + lane];
-            mma_tf32(D[i], al, bh.x, bh.y);
-            mma_tf32(D[i], ah, bl.x, bl.y);
+            mma_tf32(E[i], al, bh.x, bh.y);
             mma_tf32(D[i], ah, bh.x, bh.y);
+            mma_tf32(E[i], ah, bl.x, bl.y);
         }
     };
 
@@ -286,42 +308,49 @@ __global__ void __launch_bounds__(128, 2) loglik_mma_kernel(Plan pl, Workspace w
             }
         };
         auto compute = [&](const Raw &r, const int mt) {
-            float D[NT][4];
+            float D[NT][4], E[NT][4];
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
                 D[i][0] = nb[i][0];
                 D[i][1] = nb[i][1];
                 D[i][2] = nb[i][0];
                 D[i][3] = nb[i][1];
+                E[i][0] = E[i][1] = E[i][2] = E[i][3] = 0.f;
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                kstep(D, 2 * k, r.xa[k].x, r.xb[k].x, r.xa[k].y, r.xb[k].y);
-                kstep(D, 2 * k + 1, r.xa[k].z, r.xb[k].z, r.xa[k].w, r.xb[k].w);
+                kstep(D, E, 2 * k, r.xa[k].x, r.xb[k].x, r.xa[k].y, r.xb[k].y);
+                kstep(D, E, 2 * k + 1, r.xa[k].z, r.xb[k].z, r.xa[k].w, r.xb[k].w);
             }
-            finish(D, mt);
+            finish(D, E, mt);
         };
-        Raw r0, r1;
+        constexpr int PD = 4;  // L2 prefetch distance in m-tiles of this warp (16 frames x 512 B each)
+        auto prefetch_mt = [&](const int mt) {
+            if (VBX_L2_PREFETCH && lane == 0 && mt * 16 + 16 <= len) prefetch_l2(rho + (f0 + mt * 16) * 128, 16 * 512);
+        };
+#pragma unroll
+        for (int k = 1; k < PD; ++k) prefetch_mt(warp + 4 * k);
+        Raw r0;
         load_mt(warp, r0);
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
-        for (int mt = warp; mt < n_mt; mt += 8) {
-            load_mt(mt + 4, r1);
+        for (int mt = warp; mt < n_mt; mt += 4) {
+            prefetch_mt(mt + 4 * PD);
+            if (mt != warp) load_mt(mt, r0);
             compute(r0, mt);
-            load_mt(mt + 8, r0);
-            if (mt + 4 < n_mt) compute(r1, mt + 4);
         }
     } else {
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
         for (int mt = warp; mt < n_mt; mt += 4) {
-            float D[NT][4];
+            float D[NT][4], E[NT][4];
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
                 D[i][0] = nb[i][0];
                 D[i][1] = nb[i][1];
                 D[i][2] = nb[i][0];
                 D[i][3] = nb[i][1];
+                E[i][0] = E[i][1] = E[i][2] = E[i][3] = 0.f;
             }
             const int ra = min(mt * 16 + g, len - 1), rb = min(mt * 16 + g + 8, len - 1);
             const float *pa = rho + (f0 + ra) * R;
@@ -332,9 +361,9 @@ __global__ void __launch_bounds__(128, 2) loglik_mma_kernel(Plan pl, Workspace w
                 const int cc = min(col, R - 2);           // so only the address needs clamping
                 const float2 va = __ldg(reinterpret_cast<const float2 *>(pa + cc));
                 const float2 vb = __ldg(reinterpret_cast<const float2 *>(pb + cc));
-                kstep(D, j, va.x, vb.x, va.y, vb.y);
+                kstep(D, E, j, va.x, vb.x, va.y, vb.y);
             }
-            finish(D, mt);
+            finish(D, E, mt);
         }
     }
 }
