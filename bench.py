@@ -334,12 +334,13 @@ def main():
         torch.cuda.synchronize()
         vb.timings(reset=True)
         l0 = vb.launches
-        barrier()
-        torch.cuda.synchronize()
         sampler = ClockSampler(local_rank) if (with_clocks and rank == 0) else None
         if sampler:
             sampler.start()
             time.sleep(0.25)
+        torch.cuda.synchronize()
+        barrier()                      # every rank enters the timed region together
+        torch.cuda.synchronize()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t_wall0 = time.time()
         for i in range(steps):
@@ -352,7 +353,10 @@ def main():
         barrier()
         t_wall1 = time.time()
         clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        if os.environ.get('VBX_BENCH_DEBUG'):
+            print(f'[rank {rank}] per-step ms: {[round(x, 3) for x in per_step]} wall {1e3 * (t_wall1 - t_wall0) / steps:.3f} ms/step', file=sys.stderr, flush=True)
+        ms = sum(per_step) / steps
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
