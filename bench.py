@@ -294,10 +294,15 @@ def main():
         if world > 1:
             dist.barrier()
 
+    def dbg(msg):
+        if os.environ.get('VBX_BENCH_DEBUG'):
+            print(f'[rank {rank}] {msg}', file=sys.stderr, flush=True)
+
     def time_workload(w, wname, steps, warmup, with_clocks):
         lengths = workload_lengths(w, seed=1000 + rank)
         data = make_device_batch(lengths, w['S'], seed=17 + rank, device=device)
         N = int(lengths.sum())
+        dbg(f'{wname}: data on device, N={N}')
         vb = VbxBatch(lengths, R_DIM, w['S'], device=device)
         if args.fb_spl:
             vb.set_option('fb_states_per_lane', args.fb_spl)
@@ -332,6 +337,7 @@ def main():
                 flush.zero_()
             step()
         torch.cuda.synchronize()
+        dbg('warm-up done')
         vb.timings(reset=True)
         l0 = vb.launches
         sampler = ClockSampler(local_rank) if (with_clocks and rank == 0) else None
@@ -374,6 +380,7 @@ def main():
         return res
 
     res = time_workload(w, wname, args.steps, args.warmup, with_clocks=True)
+    dbg(f'timed region done: {res["ms"]:.3f} ms/step')
     ms, N, N_total = res['ms'], res['N'], res['N_total']
     value = N_total / (ms / 1e3)
 
@@ -450,6 +457,7 @@ def main():
                'd2h_bytes_per_step': hp.d2h_bytes, 'chunks': hp.n_chunks, 'max_abs_gamma_diff_vs_resident': dmax,
                'api': 'vbx_b200.host_pipeline.HostPipeline.run (pinned host X, gamma0 -> gamma, pi, Li on the host)'}
         del Xh, Gh, hp
+        dbg('e2e done')
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1) ----
     cpu = None

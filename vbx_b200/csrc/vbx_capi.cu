@@ -301,14 +301,16 @@ int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *
     if (h->plan.n_frames && (!X || !V || !Phi || !rho_out)) return fail(h, VBX_ERR_ARG, "vbx_prepare_project: null pointer");
     if (D < 32 || (D & 31)) return fail(h, VBX_ERR_ARG, "vbx_prepare_project: D must be a multiple of 32");
     cudaStream_t st = (cudaStream_t)stream;
-    bool done = false;
+    bool done = false, fused_g = false;
     Timed *tp = new Timed(h, st, VBX_K_PROJECT);
     if (h->opt_projection != 1) {   // auto: tcgen05 when the shape allows it (R == 128, D % 32 == 0), else FFMA tiles
         std::string why;
-        int n = vbx::launch_project_tcgen05(h->plan, X, D, V, rho_out, st, &why);
+        // the tcgen05 epilogue also emits G_t per frame into the (not yet used) rowmax scratch array
+        int n = vbx::launch_project_tcgen05(h->plan, X, D, V, Phi, rho_out, h->ws.rowmax, st, &why);
         if (n >= 0) {
             h->launches += n;
             done = true;
+            fused_g = true;
         } else if (h->opt_projection == 2) {
             delete tp;
             return fail(h, VBX_ERR_ARG, "vbx_prepare_project: tcgen05 path unavailable: " + why);
@@ -319,7 +321,8 @@ int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *
     if (rc) return rc;
     {
         Timed t(h, st, VBX_K_PREPARE);
-        rc = counted(h, vbx::launch_g_from_rho(h->plan, h->ws, rho_out, Phi, st), "g_from_rho");
+        rc = counted(h, fused_g ? vbx::launch_gsum_from_frames(h->plan, h->ws, h->ws.rowmax, st)
+                                : vbx::launch_g_from_rho(h->plan, h->ws, rho_out, Phi, st), "g_from_rho");
     }
     if (rc) return rc;
     h->prepared = true;

@@ -73,7 +73,8 @@ int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams
 int launch_mstep_mma(const Plan &pl, const Workspace &ws, const float *rho, const float *gamma, cudaStream_t st);
 int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st);
 // tcgen05 projection (vbx_project_tc.cu)
-int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, float *rho, cudaStream_t st,
-                           std::string *err);
+int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, const float *Phi, float *rho,
+                           float *gframe, cudaStream_t st, std::string *err);
+int launch_gsum_from_frames(const Plan &pl, const Workspace &ws, const float *gframe, cudaStream_t st);
 
 }  // namespace vbx

@@ -174,6 +174,24 @@ __global__ void gsum_kernel(Plan pl, Workspace ws) {
     ws.gsum[rec] = s;
 }
 
+// per-recording sum of the per-frame constants written by the tcgen05 projection epilogue (float64, fixed order)
+__global__ void __launch_bounds__(128) gsum_frames_kernel(Plan pl, Workspace ws, const float *__restrict__ gframe) {
+    const int rec = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (rec >= pl.n_rec) return;
+    const int64_t f0 = pl.offsets[rec];
+    const int T = (int)(pl.offsets[rec + 1] - f0);
+    double acc = 0.0;
+    for (int t = lane; t < T; t += 32) acc += (double)gframe[f0 + t];
+    acc = warp_sum_d(acc);
+    if (lane == 0) ws.gsum[rec] = acc;
+}
+int launch_gsum_from_frames(const Plan &pl, const Workspace &ws, const float *gframe, cudaStream_t st) {
+    if (pl.n_rec == 0) return 0;
+    gsum_frames_kernel<<<(pl.n_rec + 3) / 4, 128, 0, st>>>(pl, ws, gframe);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int launch_prepare_scale(const Plan &pl, const Workspace &ws, const float *fea, const float *Phi, float *rho,
                          cudaStream_t st) {
     if (pl.n_mtiles == 0) return 0;

@@ -63,28 +63,30 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, both K-major, kind::tf32
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, both K-major, kind::tf32.  The 64-bit shared-memory descriptors are passed as
+// (lo, hi) words: hi is a constant, lo = (address >> 4) | LBO, so the single issuing thread spends two integer adds
+// per MMA instead of rebuilding descriptors (a lone thread retires ~1 dependent instruction per 4-5 cycles).
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// K-major, 128-byte swizzle, dense 8-row groups (SBO = 1024 B), descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address
-    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
-    d |= (uint64_t)1 << 46;                            // version
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3fffu) | (1u << 16); }
+// Shared-memory matrix descriptors: K-major, 128-byte swizzle, dense 8-row groups (SBO = 1024 B), version 1 (sm_100);
+// see kDescHi / desc_lo above.
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void split_rn(const float x, float &hi, float &lo) {
     const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     hi = __uint_as_float(h);
@@ -108,12 +110,13 @@ __global__ void build_v_images_kernel(const float *__restrict__ V, int D, float 
 
 __global__ void __launch_bounds__(kThreads, 1)
 project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vimg, float *__restrict__ rho, int64_t N,
-                       int D) {
+                       int D, const float *__restrict__ Phi, float *__restrict__ gframe) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned stage buffers (required by the 128-byte swizzle)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    float *s_inv_phi = reinterpret_cast<float *>(bars + 18);   // 128 floats
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     // barrier ids
@@ -127,6 +130,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
     const int n_kb = D / kKB;
     const int64_t n_tiles = (N + kTileM - 1) / kTileM;
 
+    if (tid < 128) s_inv_phi[tid] = 1.f / Phi[tid];
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_a(s), kProducerThreads);
@@ -151,10 +155,17 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
 
     if (warp < 8) {
         // ======================= producers =======================
+        // Blocks of this CTA in order: b -> (tile = blockIdx.x + (b / n_kb) * gridDim.x, kb = b % n_kb).  Three
+        // rotating register sets keep the loads of two blocks (64 KB per SM) in flight while one is split and stored.
         const int c = tid & 7;            // 16-byte chunk inside the 128-byte row
         const int r0 = tid >> 3;          // rows r0 + 32 i, i = 0..7
-        float4 cur[8], nxt[8];
-        auto load_block = [&](int64_t tile, int kb, float4(&buf)[8]) {
+        const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t n_blocks = my_tiles * n_kb;
+        float4 bufA[8], bufB[8], bufC[8];
+        auto issue = [&](const int64_t b, float4(&buf)[8]) {
+            if (b >= n_blocks) return;
+            const int64_t tile = blockIdx.x + (b / n_kb) * gridDim.x;
+            const int kb = (int)(b % n_kb);
             const int64_t row_base = tile * kTileM;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -162,48 +173,44 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
                 buf[i] = __ldg(reinterpret_cast<const float4 *>(X + row * D + kb * kKB) + c);
             }
         };
-        int64_t tile = blockIdx.x;
-        int kb = 0;
-        if (tile < n_tiles) load_block(tile, 0, cur);
-        int s = 0;
-        uint32_t ph = 0;
-        while (tile < n_tiles) {
-            // prefetch the next block of X while this one is split and stored
-            int64_t ntile = tile;
-            int nkb = kb + 1;
-            if (nkb == n_kb) {
-                nkb = 0;
-                ntile = tile + gridDim.x;
-            }
-            if (ntile < n_tiles) load_block(ntile, nkb, nxt);
+        auto process = [&](const int64_t b, const float4(&buf)[8]) {
+            const int s = (int)(b & 1);
+            const uint32_t ph = (uint32_t)((b >> 1) & 1);
+            const int kb = (int)(b % n_kb);
             mbar_wait(empty(s), ph ^ 1);               // the MMAs that read this stage have completed
-            uint8_t *stage = smem + s * kStageBytes;
+            const uint32_t stage = smem_base + s * kStageBytes;
             if (tid == 0) {
                 mbar_expect_tx(full_b(s), 2 * kABytes);
-                bulk_g2s(smem_u32(stage + 4 * kABytes), vimg + (int64_t)kb * 2 * 4096, 2 * kABytes, full_b(s));
+                bulk_g2s(stage + 4 * kABytes, vimg + (int64_t)kb * 2 * 4096, 2 * kABytes, full_b(s));
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = r0 + 32 * i;             // 0..255
                 const int mt = r >> 7, m = r & 127;
                 float4 hi, lo;
-                split_rn(cur[i].x, hi.x, lo.x);
-                split_rn(cur[i].y, hi.y, lo.y);
-                split_rn(cur[i].z, hi.z, lo.z);
-                split_rn(cur[i].w, hi.w, lo.w);
-                const int off = m * 128 + ((c ^ (m & 7)) << 4);
-                *reinterpret_cast<float4 *>(stage + (mt * 2 + 0) * kABytes + off) = hi;
-                *reinterpret_cast<float4 *>(stage + (mt * 2 + 1) * kABytes + off) = lo;
+                split_rn(buf[i].x, hi.x, lo.x);
+                split_rn(buf[i].y, hi.y, lo.y);
+                split_rn(buf[i].z, hi.z, lo.z);
+                split_rn(buf[i].w, hi.w, lo.w);
+                const uint32_t off = (uint32_t)(m * 128 + ((c ^ (m & 7)) << 4));
+                st_shared_v4(stage + (mt * 2 + 0) * kABytes + off, hi);
+                st_shared_v4(stage + (mt * 2 + 1) * kABytes + off, lo);
             }
             fence_proxy_async_smem();                  // make the generic-proxy stores visible to the tensor core
             mbar_arrive(full_a(s));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-            tile = ntile;
-            kb = nkb;
-            if (++s == kStages) {
-                s = 0;
-                ph ^= 1;
+        };
+        issue(0, bufA);
+        issue(1, bufB);
+        for (int64_t b = 0; b < n_blocks; b += 3) {
+            issue(b + 2, bufC);
+            process(b, bufA);
+            if (b + 1 < n_blocks) {
+                issue(b + 3, bufA);
+                process(b + 1, bufB);
+            }
+            if (b + 2 < n_blocks) {
+                issue(b + 4, bufB);
+                process(b + 2, bufC);
             }
         }
     } else if (warp == 8) {
@@ -220,19 +227,20 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
                     mbar_wait(full_a(s), ph);
                     mbar_wait(full_b(s), ph);
                     tc_fence_after();
-                    const uint32_t st = smem_base + s * kStageBytes;
-                    const uint32_t b_hi = st + 4 * kABytes, b_lo = b_hi + kABytes;
+                    const uint32_t st_lo = desc_lo(smem_base + s * kStageBytes);   // descriptor word of the stage base
+                    constexpr uint32_t kImg = kABytes >> 4;                        // one operand image, in 16-byte units
+                    const uint32_t b_hi = st_lo + 4 * kImg, b_lo = b_hi + kImg;
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
-                        const uint32_t a_hi = st + (mt * 2 + 0) * kABytes, a_lo = a_hi + kABytes;
+                        const uint32_t a_hi = st_lo + (mt * 2 + 0) * kImg, a_lo = a_hi + kImg;
                         const uint32_t d = tmem_base + (uint32_t)(acc * 256 + mt * 128);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint32_t koff = ks * 32;     // 8 tf32 = 32 bytes inside the swizzle row
+                            const uint32_t koff = ks * 2;      // 8 tf32 = 32 bytes inside the swizzle row (16-byte units)
                             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                            umma_tf32(d, make_desc(a_lo + koff), make_desc(b_hi + koff), kIdesc, first);
-                            umma_tf32(d, make_desc(a_hi + koff), make_desc(b_lo + koff), kIdesc, 1u);
-                            umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + koff), kIdesc, 1u);
+                            umma_tf32(d, a_lo + koff, b_hi + koff, kDescHi, kIdesc, first);
+                            umma_tf32(d, a_hi + koff, b_lo + koff, kDescHi, kIdesc, 1u);
+                            umma_tf32(d, a_hi + koff, b_hi + koff, kDescHi, kIdesc, 1u);
                         }
                     }
                     tc_commit(empty(s));                       // stage reusable once these MMAs retire
@@ -261,6 +269,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
             for (int mt = 0; mt < 2; ++mt) {
                 const int64_t row = tile * kTileM + mt * 128 + quarter * 32 + lane;
                 float *dst = rho + row * 128;
+                float n2 = 0.f;                          // ||fea||^2 = sum_r rho^2 / Phi_r   (VBx/VBx.py:87)
 #pragma unroll 1
                 for (int cb = 0; cb < 4; ++cb) {
                     uint32_t v[32];
@@ -281,7 +290,13 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
                         for (int i = 0; i < 8; ++i)
                             *reinterpret_cast<uint4 *>(dst + cb * 32 + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float x = __uint_as_float(v[i]);
+                        n2 = fmaf(x * x, s_inv_phi[cb * 32 + i], n2);
+                    }
                 }
+                if (row < N) gframe[row] = -0.5f * (n2 + 128.f * 1.8378770664093453f);   // G_t, R = 128
             }
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));
@@ -309,8 +324,8 @@ TcState g_tc[16];
 
 }  // namespace
 
-int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, float *rho, cudaStream_t st,
-                           std::string *err) {
+int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, const float *Phi, float *rho,
+                           float *gframe, cudaStream_t st, std::string *err) {
     if (pl.R != 128) {
         if (err) *err = "tcgen05 projection needs R == 128";
         return -1;
@@ -338,7 +353,7 @@ int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V
         }
         tc.vimg_bytes = need;
     }
-    const int smem = kStages * kStageBytes + 1024 + 256;
+    const int smem = kStages * kStageBytes + 1024 + 1024;
     if (!tc.configured) {
         if (cudaFuncSetAttribute(project_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
             if (err) *err = "cudaFuncSetAttribute(smem) failed";
@@ -351,7 +366,7 @@ int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V
     build_v_images_kernel<<<D / kKB, 256, 0, st>>>(V, D, tc.vimg);
     const int64_t n_tiles = (pl.n_frames + kTileM - 1) / kTileM;
     const int grid = (int)std::min<int64_t>(n_tiles, sms);
-    project_tcgen05_kernel<<<grid, kThreads, smem, st>>>(X, tc.vimg, rho, pl.n_frames, D);
+    project_tcgen05_kernel<<<grid, kThreads, smem, st>>>(X, tc.vimg, rho, pl.n_frames, D, Phi, gframe);
     if (cudaGetLastError() != cudaSuccess) {
         if (err) *err = "tcgen05 projection launch failed";
         return -1;

@@ -1,0 +1,108 @@
+"""The steps either side of the VB-HMM call in the reference's driver, batched:
+
+  before:  x-vector transform  l2_norm(lda^T . l2_norm(x - mean1) - mean2)            VBx/vbhmm.py:125-129
+           PLDA simultaneous diagonalisation (host, once per model)                   VBx/vbhmm.py:107-113
+           projection into the PLDA space  (x - plda_mu) . plda_tr^T [:, :lda_dim]    VBx/vbhmm.py:153
+           soft initialisation from hard AHC labels  softmax(onehot * smoothing)      VBx/vbhmm.py:150-152
+  after:   hard labels  argsort(-q)[:, 0] (and 2nd best)                               VBx/vbhmm.py:160-162
+           merge_adjacent_labels + RTTM lines                                          VBx/diarization_lib.py:113-135, vbhmm.py:48-51
+
+The dense algebra runs on the device through torch (library GEMMs: not the hot path); the label merge is a
+host-side O(T) pass exactly like the reference's.  AHC itself (VBx/vbhmm.py:131-146) is out of scope.
+"""
+import numpy as np
+import torch
+
+
+def diagonalise_plda(plda_mu, plda_tr, plda_psi):
+    """VBx/vbhmm.py:107-113: generalised eigen-problem B v = lambda W v; returns (mu, tr, psi) with psi descending."""
+    from scipy.linalg import eigh
+    W = np.linalg.inv(plda_tr.T.dot(plda_tr))
+    B = np.linalg.inv((plda_tr.T / plda_psi).dot(plda_tr))
+    acvar, wccn = eigh(B, W)
+    return plda_mu, wccn.T[::-1].copy(), acvar[::-1].copy()
+
+
+def l2_norm_rows(x):
+    """VBx/diarization_lib.py:172-187 for a matrix of row vectors."""
+    return x / torch.linalg.vector_norm(x, dim=1, keepdim=True)
+
+
+def xvector_transform(x_raw, mean1, mean2, lda):
+    """VBx/vbhmm.py:129 on the device.  x_raw [N,256] -> [N,128] (float64 like the reference's h5 arrays)."""
+    x = l2_norm_rows(x_raw - mean1[None, :])
+    x = x @ lda - mean2[None, :]
+    return l2_norm_rows(x)
+
+
+def plda_project(x, plda_mu, plda_tr, lda_dim):
+    """VBx/vbhmm.py:153: fea = (x - plda_mu) . plda_tr^T, first lda_dim columns."""
+    return ((x - plda_mu[None, :]) @ plda_tr.T)[:, :lda_dim]
+
+
+def soft_init(labels, n_states, smoothing):
+    """VBx/vbhmm.py:150-152: qinit = softmax(onehot(labels) * smoothing) (rows), float32 on labels' device."""
+    q = torch.zeros((labels.shape[0], n_states), dtype=torch.float32, device=labels.device)
+    q.scatter_(1, labels.long()[:, None], float(smoothing))
+    return torch.softmax(q, dim=1)
+
+
+def hard_labels(gamma, second=False):
+    """VBx/vbhmm.py:160-162: most (and second most) likely speaker per frame.  Stable ordering like np.argsort(-q)."""
+    order = torch.argsort(gamma, dim=1, descending=True, stable=True)
+    return (order[:, 0], order[:, 1]) if second and gamma.shape[1] > 1 else order[:, 0]
+
+
+def merge_adjacent_labels(starts, ends, labels):
+    """Compact labelled segments: merge adjacent/overlapping segments with equal labels, split the overlap of
+    differently labelled neighbours in the middle.  Same result as VBx/diarization_lib.py:113-135."""
+    starts = np.asarray(starts, dtype=np.float64)
+    ends = np.asarray(ends, dtype=np.float64)
+    labels = np.asarray(labels)
+    if len(labels) == 0:
+        return starts.copy(), ends.copy(), labels.copy()
+    touching = np.isclose(ends[:-1], starts[1:]) | (ends[:-1] > starts[1:])
+    cut = np.nonzero(~touching | (labels[1:] != labels[:-1]))[0]        # a new segment starts at cut+1
+    first = np.concatenate([[0], cut + 1])
+    last = np.concatenate([cut, [len(labels) - 1]])
+    s, e, l = starts[first].copy(), ends[last].copy(), labels[first].copy()
+    over = np.nonzero(s[1:] < e[:-1])[0]
+    mid = (e[over] + s[over + 1]) / 2.0
+    e[over] = mid
+    s[over + 1] = mid
+    return s, e, l
+
+
+def rttm_lines(recording, starts, ends, labels):
+    """VBx/vbhmm.py:48-51."""
+    return [f'SPEAKER {recording} 1 {s:03f} {e - s:03f} <NA> <NA> {int(l) + 1} <NA> <NA>'
+            for s, e, l in zip(starts, ends, labels)]
+
+
+def diarize_recording(x_raw, seg_times, ahc_labels, transform, plda, Fa, Fb, loopP, lda_dim=128, smoothing=5.0,
+                      max_iters=40, epsilon=1e-6, device=None, recording='rec'):
+    """One recording end to end on the device, the AHC+VB branch of VBx/vbhmm.py:120-172 given the AHC labels.
+    transform = (mean1, mean2, lda); plda = (mu, tr, psi) as read from the Kaldi model (not yet diagonalised).
+    Returns (rttm lines, labels, gamma)."""
+    from .batch import VbxBatch
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    mean1, mean2, lda = (f64(a) for a in transform)
+    mu, tr, psi = diagonalise_plda(*plda)
+    x = xvector_transform(f64(x_raw), mean1, mean2, lda)
+    fea = plda_project(x, f64(mu), f64(tr), lda_dim)
+    S = int(np.max(ahc_labels)) + 1
+    q0 = soft_init(torch.from_numpy(np.asarray(ahc_labels)).to(dev), S, smoothing)
+    T = fea.shape[0]
+    vb = VbxBatch([T], lda_dim, S, device=dev)
+    vb.set_option('gemm', 1)
+    g = torch.zeros((T, vb.S), dtype=torch.float32, device=dev)
+    g[:, :S] = q0
+    p = torch.zeros((1, vb.S), dtype=torch.float32, device=dev)
+    p[0, :S] = 1.0 / S
+    vb.prepare_scale(fea.float().contiguous(), f64(psi[:lda_dim]).float())
+    vb.run(g, p, Fa=Fa, Fb=Fb, loopProb=loopP, maxIters=max_iters, epsilon=epsilon)
+    labels = hard_labels(g[:, :S]).cpu().numpy()
+    s, e, l = merge_adjacent_labels(seg_times[:, 0], seg_times[:, 1], labels)
+    vb.close()
+    return rttm_lines(recording, s, e, l), labels, g[:, :S]
