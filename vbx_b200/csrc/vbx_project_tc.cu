@@ -10,7 +10,9 @@
 //   warp  8    MMA issuer: one thread issues 24 tcgen05.mma (M128 x N128 x K8, kind::tf32) per 32-column block
 //              (2 M-tiles x 4 k-steps x 3 split terms); tcgen05.commit releases the smem stage / publishes the
 //              accumulator.
-//   warps 9-12 epilogue: tcgen05.ld the 2 x (128 x 128) fp32 accumulators out of TMEM and store rho.
+//   warps 9-16 epilogue: tcgen05.ld the 2 x (128 x 128) fp32 accumulators out of TMEM (lane = row), accumulate the
+//              per-frame constant G_t, transpose through a swizzled shared-memory tile and store rho with full
+//              128-byte lines per row.
 // Shared memory: 2 stages x (A hi/lo for 2 M-tiles 64 KB + B hi/lo 32 KB) = 192 KB.  TMEM: 2 accumulator sets of
 // 256 columns (all 512), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
@@ -27,7 +29,9 @@ constexpr int kStages = 2;
 constexpr int kABytes = 128 * 128;          // one 128-row x 128-byte operand image
 constexpr int kStageBytes = 4 * kABytes + 2 * kABytes;  // A: 2 mtiles x hi/lo, B: hi/lo
 constexpr int kProducerThreads = 256;
-constexpr int kThreads = 13 * 32;
+constexpr int kEpiWarps = 8;                // two per TMEM lane quarter (one per M-tile)
+constexpr int kThreads = (9 + kEpiWarps) * 32;
+constexpr int kEpiStageBytes = 32 * 128;    // per epilogue warp: 32 rows x 32 columns, 16-byte-chunk XOR swizzle
 constexpr uint32_t kTmemCols = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -84,6 +88,13 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+// streaming 16-byte load that does not allocate in L1: with 194 KB of shared memory only ~32 KB of L1 remain, and
+// allocating loads would cap the bytes in flight at that size
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -139,7 +150,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
-            mbar_init(tmem_empty(a), 128);
+            mbar_init(tmem_empty(a), kEpiWarps * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -155,13 +166,13 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
 
     if (warp < 8) {
         // ======================= producers =======================
-        // Blocks of this CTA in order: b -> (tile = blockIdx.x + (b / n_kb) * gridDim.x, kb = b % n_kb).  Three
-        // rotating register sets keep the loads of two blocks (64 KB per SM) in flight while one is split and stored.
+        // Blocks of this CTA in order: b -> (tile = blockIdx.x + (b / n_kb) * gridDim.x, kb = b % n_kb).  Two
+        // ping-pong register sets keep the loads of the next block in flight while one is split and stored.
         const int c = tid & 7;            // 16-byte chunk inside the 128-byte row
         const int r0 = tid >> 3;          // rows r0 + 32 i, i = 0..7
         const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t n_blocks = my_tiles * n_kb;
-        float4 bufA[8], bufB[8], bufC[8];
+        float4 bufA[8], bufB[8];
         auto issue = [&](const int64_t b, float4(&buf)[8]) {
             if (b >= n_blocks) return;
             const int64_t tile = blockIdx.x + (b / n_kb) * gridDim.x;
@@ -170,7 +181,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int64_t row = min(row_base + r0 + 32 * i, N - 1);
-                buf[i] = __ldg(reinterpret_cast<const float4 *>(X + row * D + kb * kKB) + c);
+                buf[i] = ldg_stream(reinterpret_cast<const float4 *>(X + row * D + kb * kKB) + c);
             }
         };
         auto process = [&](const int64_t b, const float4(&buf)[8]) {
@@ -200,17 +211,12 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
             mbar_arrive(full_a(s));
         };
         issue(0, bufA);
-        issue(1, bufB);
-        for (int64_t b = 0; b < n_blocks; b += 3) {
-            issue(b + 2, bufC);
+        for (int64_t b = 0; b < n_blocks; b += 2) {
+            issue(b + 1, bufB);
             process(b, bufA);
             if (b + 1 < n_blocks) {
-                issue(b + 3, bufA);
+                issue(b + 2, bufA);
                 process(b + 1, bufB);
-            }
-            if (b + 2 < n_blocks) {
-                issue(b + 4, bufB);
-                process(b + 2, bufC);
             }
         }
     } else if (warp == 8) {
@@ -260,44 +266,59 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
     } else {
         // ======================= epilogue =======================
         const int quarter = warp & 3;                  // TMEM lanes 32*quarter .. +31 are visible to this warp
+        const int mt = (warp - 9) >> 2;                // M-tile handled by this warp
+        const uint32_t epi = smem_base + kStages * kStageBytes + 1024 + (warp - 9) * kEpiStageBytes;
+        const uint32_t inv_phi_s = smem_u32(s_inv_phi);
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(tmem_full(acc), acc_ph);
             tc_fence_after();
+            const int64_t row_base = tile * kTileM + mt * 128 + quarter * 32;
+            float n2 = 0.f;                              // ||fea||^2 = sum_r rho^2 / Phi_r   (VBx/VBx.py:87)
 #pragma unroll 1
-            for (int mt = 0; mt < 2; ++mt) {
-                const int64_t row = tile * kTileM + mt * 128 + quarter * 32 + lane;
-                float *dst = rho + row * 128;
-                float n2 = 0.f;                          // ||fea||^2 = sum_r rho^2 / Phi_r   (VBx/VBx.py:87)
-#pragma unroll 1
-                for (int cb = 0; cb < 4; ++cb) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + mt * 128 + cb * 32);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr)
-                        : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (row < N) {
+            for (int cb = 0; cb < 4; ++cb) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + mt * 128 + cb * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // lane = row: G_t partial sum and the swizzled stage (chunk j of row r at position j ^ (r & 7))
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            *reinterpret_cast<uint4 *>(dst + cb * 32 + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = __uint_as_float(v[i]);
-                        n2 = fmaf(x * x, s_inv_phi[cb * 32 + i], n2);
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    float4 ip;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ip.x), "=f"(ip.y), "=f"(ip.z), "=f"(ip.w)
+                                 : "r"(inv_phi_s + (uint32_t)(cb * 32 + 4 * j) * 4));
+                    const float4 x = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    n2 = fmaf(x.x * x.x, ip.x, n2);
+                    n2 = fmaf(x.y * x.y, ip.y, n2);
+                    n2 = fmaf(x.z * x.z, ip.z, n2);
+                    n2 = fmaf(x.w * x.w, ip.w, n2);
+                    st_shared_v4(epi + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), x);
                 }
-                if (row < N) gframe[row] = -0.5f * (n2 + 128.f * 1.8378770664093453f);   // G_t, R = 128
+                __syncwarp();
+                // 8 lanes cover the 128 bytes of one row: every store instruction writes 4 full lines
+                const int cc = lane & 7, rr = lane >> 3;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = 4 * k + rr;
+                    float4 x;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                                 : "r"(epi + (uint32_t)(r * 128 + ((cc ^ (r & 7)) << 4))));
+                    if (row_base + r < N) *reinterpret_cast<float4 *>(rho + (row_base + r) * 128 + cb * 32 + 4 * cc) = x;
+                }
+                __syncwarp();
             }
+            if (row_base + lane < N) gframe[row_base + lane] = -0.5f * (n2 + 128.f * 1.8378770664093453f);   // G_t, R = 128
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));
             if (++acc == 2) {
@@ -353,7 +374,7 @@ int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V
         }
         tc.vimg_bytes = need;
     }
-    const int smem = kStages * kStageBytes + 1024 + 1024;
+    const int smem = kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes + 1024;
     if (!tc.configured) {
         if (cudaFuncSetAttribute(project_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
             if (err) *err = "cudaFuncSetAttribute(smem) failed";
