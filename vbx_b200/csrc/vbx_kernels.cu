@@ -640,8 +640,8 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
                                                                float *pi_io, const int32_t *__restrict__ n_states) {
     constexpr int LPR = S_PAD / SPL;
     constexpr int RPW = 32 / LPR;
-    constexpr int PF = (SPL == 4) ? 8 : 16;  // frames per prefetch burst, forward sweep (ping-pong register sets)
-    constexpr int PB = (SPL == 4) ? 4 : 8;   // ... backward sweep (three arrays per frame)
+    constexpr int PF = (SPL == 4) ? 8 : (SPL == 2 ? 24 : 16);  // frames per prefetch burst, forward sweep (ping-pong register sets)
+    constexpr int PB = (SPL == 4) ? 4 : (SPL == 2 ? 10 : 8);   // ... backward sweep (three arrays per frame)
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int g = lane / LPR, l = lane % LPR;
