@@ -98,6 +98,17 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
             float *alpha_io, float *invL_io, int32_t warm_start, double *Li_out, int32_t *n_iters_out,
             int32_t *flags_out, void *stream);
 
+/* Float64 evaluation of the same EM loop ("exact" mode for the one-recording-per-call use of VBx/vbhmm.py:154-158,
+ * where the reference stops on an ELBO improvement < 1e-6, VBx/vbhmm.py:157 -- below float32 resolution).
+ * All arrays float64: fea [N,R] (the reference's X, VBx/VBx.py:30), Phi [R], gamma_io [N,S], pi_io [n_rec,S],
+ * alpha_io / invL_io [n_rec,S,R] or NULL, Li_out [n_rec,max_iters].  Needs vbx_plan only (no vbx_prepare_*, no float32
+ * workspace); `workspace` must hold vbx_f64_workspace_bytes() bytes.  Simple kernels, not tuned for throughput. */
+int vbx_f64_workspace_bytes(vbx_handle_t h, size_t *bytes_out);
+int vbx_run_f64(vbx_handle_t h, void *workspace, size_t workspace_bytes, const double *fea, const double *Phi,
+                double *gamma_io, double *pi_io, const int32_t *n_states, double Fa, double Fb, double loop_prob,
+                int32_t max_iters, double epsilon, double *alpha_io, double *invL_io, int32_t warm_start,
+                double *Li_out, int32_t *n_iters_out, int32_t *flags_out, void *stream);
+
 /* Number of kernels launched by this handle since creation (bench.py reports it as gpu_launches). */
 int64_t vbx_launch_count(vbx_handle_t h);
 

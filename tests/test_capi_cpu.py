@@ -21,7 +21,7 @@ def lib():
 def header_functions():
     src = open(os.path.join(ROOT, 'include', 'vbx_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    return sorted(set(re.findall(r'\b(vbx_[a-z_]+)\s*\(', src)))
+    return sorted(set(re.findall(r'\b(vbx_[a-z0-9_]+)\s*\(', src)))
 
 
 def test_library_exports_every_declared_symbol(lib):

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, 'libvbx_b200.so')
 
 EXPORTS = ['vbx_version', 'vbx_padded_states', 'vbx_create', 'vbx_destroy', 'vbx_last_error',
            'vbx_set_option', 'vbx_plan', 'vbx_bind_workspace', 'vbx_prepare_scale',
-           'vbx_prepare_project', 'vbx_run', 'vbx_launch_count', 'vbx_get_timings']
+           'vbx_prepare_project', 'vbx_run', 'vbx_launch_count', 'vbx_get_timings', 'vbx_f64_workspace_bytes',
+           'vbx_run_f64']
 
 FLAG_NONFINITE, FLAG_ELBO_DECREASED, FLAG_CONVERGED = 1, 2, 4
 KERNEL_CLASSES = ['project', 'prepare', 'run_init', 'mstep_partial', 'speaker_model', 'loglik', 'forward_backward']
@@ -58,6 +59,10 @@ def load():
     lib.vbx_run.argtypes = [vp, vp, vp, vp, vp, vp, dbl, dbl, dbl, i32, dbl, vp, vp, i32, vp, vp, vp, vp]
     lib.vbx_launch_count.restype = i64
     lib.vbx_launch_count.argtypes = [vp]
+    lib.vbx_f64_workspace_bytes.restype = ctypes.c_int
+    lib.vbx_f64_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    lib.vbx_run_f64.restype = ctypes.c_int
+    lib.vbx_run_f64.argtypes = [vp, vp, ctypes.c_size_t, vp, vp, vp, vp, vp, dbl, dbl, dbl, i32, dbl, vp, vp, i32, vp, vp, vp, vp]
     lib.vbx_get_timings.restype = ctypes.c_int
     lib.vbx_get_timings.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(i64), i32]
     _lib = lib

@@ -4,11 +4,25 @@ Same positional/keyword arguments, same `(gamma, pi, Li[, alpha, invL])` return 
 arrays, same exceptions for bad arguments; the work itself happens in the CUDA library.  The
 reference's single call site is VBx/vbhmm.py:154-158.
 """
+import os
+
 import numpy as np
 import torch
 
 from . import _lib
-from .batch import VbxBatch
+from .batch import VbxBatch, run_f64
+
+# Arithmetic of the drop-in call.  'float64' (default): every quantity in float64 on the GPU, reproduces the
+# reference's iteration count and values to ~1e-9 (VBx/vbhmm.py:157 stops on an ELBO step of 1e-6).  'float32': the
+# fast kernels of the batched path (within 1e-4 relative; the stop rule may fire a few iterations early for tiny epsilon).
+PRECISION = os.environ.get('VBX_B200_PRECISION', 'float64')
+
+
+def set_precision(name):
+    global PRECISION
+    if name not in ('float32', 'float64'):
+        raise ValueError("precision must be 'float32' or 'float64'")
+    PRECISION = name
 
 
 def _der_diagnostic(q, ref, expected=True, xentropy=False):
@@ -31,8 +45,8 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
         return_model=False, alpha=None, invL=None):
     """See VBx/VBx.py:30-68 for the meaning of every argument (kept identical).
 
-    Differences from the reference, all below its own numerical noise floor for diarization:
-    arithmetic is float32 on the GPU (ELBO accumulated in float64); outputs are float64 numpy."""
+    Runs on the GPU in float64 by default (module variable PRECISION / env VBX_B200_PRECISION; 'float32' selects the
+    fast kernels of the batched path); outputs are float64 numpy like the reference's."""
     X = np.asarray(X)
     Phi = np.asarray(Phi)
     T, D = X.shape                                    # VBx/VBx.py:74
@@ -49,6 +63,8 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
     dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
     if dev is None:
         raise _lib.VbxError('VBx(): no CUDA device - vbx_b200 has no CPU fallback')
+    if PRECISION == 'float64':
+        return _vbx_f64(X, Phi, loopProb, Fa, Fb, pi, gamma, maxIters, epsilon, ref, return_model, alpha, invL, dev)
     vb = VbxBatch([T], D, S, device=dev)
     vb.set_option('gemm', 1)      # single recording: float32 FFMA contractions (closest to the float64 reference);
     Sp = vb.S                     # the batched API defaults to tensor cores in split-precision 3xTF32
@@ -95,5 +111,53 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
     res = (gamma_out, pi_out, Li)
     if return_model:
         res = res + (out['alpha'][0, :S].double().cpu().numpy(), out['invL'][0, :S].double().cpu().numpy())
+    vb.close()
+    return res
+
+
+def _vbx_f64(X, Phi, loopProb, Fa, Fb, pi, gamma, maxIters, epsilon, ref, return_model, alpha, invL, dev):
+    """Float64 evaluation through vbx_run_f64 (include/vbx_b200.h)."""
+    T, D = X.shape
+    S = len(pi)
+    vb = VbxBatch([T], D, S, device=dev, allocate=False)
+    Sp = vb.S
+    f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    fea_d, phi_d = f64(X), f64(Phi)
+    g = torch.zeros((T, Sp), dtype=torch.float64, device=dev)
+    g[:, :S] = f64(gamma)
+    p = torch.zeros((1, Sp), dtype=torch.float64, device=dev)
+    p[0, :S] = f64(pi)
+    warm = alpha is not None and invL is not None
+    kw = {}
+    if warm:
+        a = torch.zeros((1, Sp, D), dtype=torch.float64, device=dev)
+        il = torch.zeros((1, Sp, D), dtype=torch.float64, device=dev)
+        a[0, :S] = f64(alpha)
+        il[0, :S] = f64(invL)
+        kw = dict(alpha=a, invL=il, warm_start=True)
+    flags, out = 0, None
+    if ref is None:
+        out = run_f64(vb, fea_d, phi_d, g, p, Fa=Fa, Fb=Fb, loopProb=loopProb, maxIters=maxIters, epsilon=epsilon,
+                      return_model=return_model, **kw)
+        n = int(out['n_iters'][0].item())
+        flags = int(out['flags'][0].item())
+        Li = [[float(v)] for v in out['Li'][0, :n].cpu().numpy()]
+    else:
+        Li = []
+        for ii in range(maxIters):     # one iteration per call so that DER() can look at gamma (VBx/VBx.py:108-109)
+            out = run_f64(vb, fea_d, phi_d, g, p, Fa=Fa, Fb=Fb, loopProb=loopProb, maxIters=1, epsilon=epsilon,
+                          return_model=return_model, **(kw if ii == 0 else {}))
+            elbo = float(out['Li'][0, 0].item())
+            gh = g[:, :S].cpu().numpy()
+            Li.append([elbo, DER(gh, ref), DER(gh, ref, xentropy=True)])
+            if ii > 0 and elbo - Li[-2][0] < epsilon:
+                if elbo - Li[-2][0] < 0:
+                    flags |= _lib.FLAG_ELBO_DECREASED
+                break
+    if flags & _lib.FLAG_ELBO_DECREASED:
+        print('WARNING: Value of auxiliary function has decreased!')   # VBx/VBx.py:123-124
+    res = (g[:, :S].cpu().numpy(), p[0, :S].cpu().numpy(), Li)
+    if return_model:
+        res = res + (out['alpha'][0, :S].cpu().numpy(), out['invL'][0, :S].cpu().numpy())
     vb.close()
     return res

@@ -160,6 +160,35 @@ class VbxBatch:
         return out
 
 
+def run_f64(vb, fea, Phi, gamma, pi, Fa=1.0, Fb=1.0, loopProb=0.9, maxIters=10, epsilon=1e-4, alpha=None, invL=None,
+            warm_start=False, return_model=False):
+    """Float64 evaluation of the EM loop on the planned batch `vb` (VbxBatch(..., allocate=False) is enough).
+    fea [N,R], Phi [R], gamma [N,S], pi [B,S] float64 CUDA tensors (gamma, pi updated in place)."""
+    dev = vb.device
+    for t, shape, name in ((fea, (vb.N, vb.R), 'fea'), (Phi, (vb.R,), 'Phi'), (gamma, (vb.N, vb.S), 'gamma'), (pi, (vb.B, vb.S), 'pi')):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == shape):
+            raise ValueError(f'{name}: expected a contiguous float64 CUDA tensor of shape {shape}')
+    need = ctypes.c_size_t()
+    vb._check(vb.lib.vbx_f64_workspace_bytes(vb._h, ctypes.byref(need)))
+    ws = torch.empty(int(need.value), dtype=torch.uint8, device=dev)
+    if return_model or warm_start:
+        if alpha is None:
+            alpha = torch.zeros((vb.B, vb.S, vb.R), dtype=torch.float64, device=dev)
+        if invL is None:
+            invL = torch.zeros((vb.B, vb.S, vb.R), dtype=torch.float64, device=dev)
+    Li = torch.empty((vb.B, max(int(maxIters), 1)), dtype=torch.float64, device=dev)
+    n_iters = torch.empty(vb.B, dtype=torch.int32, device=dev)
+    flags = torch.empty(vb.B, dtype=torch.int32, device=dev)
+    vb._check(vb.lib.vbx_run_f64(vb._h, _ptr(ws), ws.numel(), _ptr(fea), _ptr(Phi), _ptr(gamma), _ptr(pi), _ptr(vb.n_states),
+                                 float(Fa), float(Fb), float(loopProb), int(maxIters), float(epsilon), _ptr(alpha), _ptr(invL),
+                                 int(bool(warm_start)), _ptr(Li), _ptr(n_iters), _ptr(flags), vb._stream()))
+    torch.cuda.current_stream(dev).synchronize()     # ws is released when this function returns
+    out = dict(gamma=gamma, pi=pi, Li=Li[:, :int(maxIters)], n_iters=n_iters, flags=flags)
+    if return_model or warm_start:
+        out.update(alpha=alpha, invL=invL)
+    return out
+
+
 def vbx_batch(fea, Phi, lengths, gamma, pi=None, n_states=None, loopProb=0.9, Fa=1.0, Fb=1.0, maxIters=10,
               epsilon=1e-4, return_model=False, alpha=None, invL=None):
     """One-call batched VBx on CUDA tensors.

@@ -386,6 +386,33 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
     return VBX_OK;
 }
 
+int vbx_f64_workspace_bytes(vbx_handle_t h, size_t *bytes_out) {
+    if (!h || !bytes_out) return VBX_ERR_ARG;
+    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_f64_workspace_bytes: call vbx_plan first");
+    *bytes_out = vbx::f64_workspace_bytes(h->plan);
+    return VBX_OK;
+}
+
+int vbx_run_f64(vbx_handle_t h, void *workspace, size_t workspace_bytes, const double *fea, const double *Phi,
+                double *gamma_io, double *pi_io, const int32_t *n_states, double Fa, double Fb, double loop_prob,
+                int32_t max_iters, double epsilon, double *alpha_io, double *invL_io, int32_t warm_start,
+                double *Li_out, int32_t *n_iters_out, int32_t *flags_out, void *stream) {
+    if (!h) return VBX_ERR_ARG;
+    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_run_f64: call vbx_plan first");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    const vbx::Plan &pl = h->plan;
+    if (pl.n_rec == 0) return VBX_OK;
+    if (!workspace || workspace_bytes < vbx::f64_workspace_bytes(pl)) return fail(h, VBX_ERR_STATE, "vbx_run_f64: workspace too small");
+    if (max_iters < 0 || !(Fb != 0.0)) return fail(h, VBX_ERR_ARG, "vbx_run_f64: bad max_iters / Fb");
+    if (!Li_out || !n_iters_out || !flags_out || !pi_io || (pl.n_frames && (!fea || !Phi || !gamma_io)))
+        return fail(h, VBX_ERR_ARG, "vbx_run_f64: null pointer");
+    if (warm_start && (!alpha_io || !invL_io)) return fail(h, VBX_ERR_ARG, "vbx_run_f64: warm_start needs alpha_io and invL_io");
+    return counted(h, vbx::launch_run_f64(pl, workspace, fea, Phi, gamma_io, pi_io, n_states, Fa, Fb, loop_prob, max_iters, epsilon,
+                                          alpha_io, invL_io, warm_start, Li_out, n_iters_out, flags_out, (cudaStream_t)stream),
+                   "run_f64");
+}
+
 int64_t vbx_launch_count(vbx_handle_t h) { return h ? h->launches : -1; }
 
 int vbx_get_timings(vbx_handle_t h, double *ms_out, int64_t *count_out, int32_t reset) {

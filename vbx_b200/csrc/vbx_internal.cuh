@@ -72,6 +72,12 @@ int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams
 // tensor-core (mma.sync 3xTF32) versions of the two in-loop contractions (vbx_mma_kernels.cu)
 int launch_mstep_mma(const Plan &pl, const Workspace &ws, const float *rho, const float *gamma, cudaStream_t st);
 int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st);
+// float64 "exact" path (vbx_f64.cu)
+size_t f64_workspace_bytes(const Plan &pl);
+int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const double *Phi, double *gamma, double *pi,
+                   const int32_t *n_states, double Fa, double Fb, double loopP, int max_iters, double epsilon,
+                   double *alpha_io, double *invL_io, int warm, double *Li, int32_t *n_iters, int32_t *flags,
+                   cudaStream_t st);
 // tcgen05 projection (vbx_project_tc.cu)
 int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, const float *Phi, float *rho,
                            float *gframe, cudaStream_t st, std::string *err);
