@@ -189,6 +189,34 @@ def test_state_counts_vs_oracle(S):
     check_elbo(out['Li'], ref['Li'])
 
 
+@pytest.mark.parametrize('S', [6, 16, 30, 64])
+def test_long_recordings_chunked_scan(S):
+    """Recordings of >= 4096 frames take the chunked-scan forward-backward (three phases per sweep); mixed with short
+    ones in the same batch.  Same parity bar against the oracle."""
+    lens = np.array([4096, 300, 5000, 4097, 1, 9000 if S <= 16 else 4500])
+    d = synth.make_batch(lens, R=128, S=S, seed=90 + S, dtype=np.float32)
+    ns = np.full(len(lens), S, dtype=np.int32)
+    ns[2] = max(2, S - 3)
+    g0 = d['gamma0'].astype(np.float64)
+    lo, hi = d['offsets'][2], d['offsets'][3]
+    g0[lo:hi, ns[2]:] = 0
+    g0[lo:hi] /= g0[lo:hi].sum(1, keepdims=True)
+    pi0 = np.zeros((len(lens), S))
+    for b in range(len(lens)):
+        pi0[b, :ns[b]] = 1.0 / ns[b]
+    kw = dict(Fa=0.2, Fb=6.0, loopProb=0.35) if S == 30 else dict(Fa=0.3, Fb=17.0, loopProb=0.99)
+    ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], g0, pi0, kw['Fa'], kw['Fb'], kw['loopProb'], 6, -np.inf, n_states=ns)
+    out = run_gpu(d['fea'], d['Phi'], lens, g0.astype(np.float32), n_states=ns, maxIters=6, epsilon=-np.inf, **kw)
+    assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
+    assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
+    check_elbo(out['Li'], ref['Li'])
+    assert np.abs(out['gamma'].sum(1) - 1).max() < 1e-5
+    # a long recording alone == inside the batch, bit for bit
+    lo, hi = d['offsets'][0], d['offsets'][1]
+    one = run_gpu(d['fea'][lo:hi], d['Phi'], [hi - lo], g0[lo:hi].astype(np.float32), maxIters=6, epsilon=-np.inf, **kw)
+    assert np.array_equal(one['gamma'], out['gamma'][lo:hi]) and np.array_equal(one['Li'][0], out['Li'][0])
+
+
 def test_small_feature_dims():
     for R in (16, 32, 64):
         lens, d = ragged_batch(6, 5, seed=50 + R, tmax=200, R=R)

@@ -69,12 +69,25 @@ size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
     }
     w.bias = c.take<float>(B * S);
     w.occ = c.take<float>(B * S);
-    w.reg = c.take<double>(B);
+    w.regp = c.take<double>(B * S);
     w.gsum = c.take<double>(B);
     w.gpart = c.take<double>((size_t)pl.n_mtiles);
     w.prev_elbo = c.take<double>(B);
     w.active = c.take<int32_t>(B);
     w.scratch = c.take<float>(2 * vbx::kMaxS);
+    {
+        const size_t LC = (size_t)pl.n_lchunks;
+        w.fa_u = c.take<float>(LC * S * S);
+        w.fa_lam = c.take<float>(LC * S);
+        w.fa_exp = c.take<float>(LC * S);
+        w.astart = c.take<float>(LC * S);
+        w.bb_v = c.take<float>(LC * S * S);
+        w.bb_mu = c.take<float>(LC * S);
+        w.bb_exp = c.take<float>(LC * S);
+        w.beta = c.take<float>(LC * S);
+        w.occp = c.take<float>(LC * S);
+        w.entp = c.take<float>(LC * S);
+    }
     if (ws) *ws = w;
     return c.off + 256;
 }
@@ -179,6 +192,21 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
         }
     }
     mbegin[n_rec] = (int32_t)mrec.size();
+    // long recordings -> chunk lists of the chunked-scan forward-backward
+    std::vector<int32_t> lrec_list, lrec_first(std::max(n_rec, 1), 0), lrec_nchunks(std::max(n_rec, 1), 0), lchunk_rec, lchunk_idx;
+    for (int b = 0; b < n_rec; ++b) {
+        const int64_t T = offsets_host[b + 1] - offsets_host[b];
+        if (T >= vbx::kLongT) {
+            const int K = (int)((T + vbx::kChunk - 1) / vbx::kChunk);
+            lrec_list.push_back(b);
+            lrec_first[b] = (int32_t)lchunk_rec.size();
+            lrec_nchunks[b] = K;
+            for (int k = 0; k < K; ++k) {
+                lchunk_rec.push_back(b);
+                lchunk_idx.push_back(k);
+            }
+        }
+    }
 
     // one device blob for all plan arrays
     size_t off = 0;
@@ -194,6 +222,11 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
     const size_t o_mrec = reserve(sizeof(int32_t) * std::max<size_t>(mrec.size(), 1));
     const size_t o_mf0 = reserve(sizeof(int64_t) * std::max<size_t>(mf0.size(), 1));
     const size_t o_mb = reserve(sizeof(int32_t) * (n_rec + 1));
+    const size_t o_ll = reserve(sizeof(int32_t) * std::max<size_t>(lrec_list.size(), 1));
+    const size_t o_lf = reserve(sizeof(int32_t) * lrec_first.size());
+    const size_t o_ln = reserve(sizeof(int32_t) * lrec_nchunks.size());
+    const size_t o_lcr = reserve(sizeof(int32_t) * std::max<size_t>(lchunk_rec.size(), 1));
+    const size_t o_lci = reserve(sizeof(int32_t) * std::max<size_t>(lchunk_idx.size(), 1));
     if (h->plan_mem) {
         cudaFree(h->plan_mem);
         h->plan_mem = nullptr;
@@ -211,7 +244,12 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
         (e = up(o_lf0, lf0.data(), sizeof(int64_t) * lf0.size())) != cudaSuccess ||
         (e = up(o_mrec, mrec.data(), sizeof(int32_t) * mrec.size())) != cudaSuccess ||
         (e = up(o_mf0, mf0.data(), sizeof(int64_t) * mf0.size())) != cudaSuccess ||
-        (e = up(o_mb, mbegin.data(), sizeof(int32_t) * (n_rec + 1))) != cudaSuccess)
+        (e = up(o_mb, mbegin.data(), sizeof(int32_t) * (n_rec + 1))) != cudaSuccess ||
+        (e = up(o_ll, lrec_list.data(), sizeof(int32_t) * lrec_list.size())) != cudaSuccess ||
+        (e = up(o_lf, lrec_first.data(), sizeof(int32_t) * lrec_first.size())) != cudaSuccess ||
+        (e = up(o_ln, lrec_nchunks.data(), sizeof(int32_t) * lrec_nchunks.size())) != cudaSuccess ||
+        (e = up(o_lcr, lchunk_rec.data(), sizeof(int32_t) * lchunk_rec.size())) != cudaSuccess ||
+        (e = up(o_lci, lchunk_idx.data(), sizeof(int32_t) * lchunk_idx.size())) != cudaSuccess)
         return cuda_fail(h, e, "cudaMemcpy(plan)");
 
     vbx::Plan &pl = h->plan;
@@ -229,6 +267,13 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
     pl.mtile_rec = reinterpret_cast<const int32_t *>(base + o_mrec);
     pl.mtile_f0 = reinterpret_cast<const int64_t *>(base + o_mf0);
     pl.mtile_begin = reinterpret_cast<const int32_t *>(base + o_mb);
+    pl.n_lrec = (int32_t)lrec_list.size();
+    pl.n_lchunks = (int32_t)lchunk_rec.size();
+    pl.lrec_list = reinterpret_cast<const int32_t *>(base + o_ll);
+    pl.lrec_first = reinterpret_cast<const int32_t *>(base + o_lf);
+    pl.lrec_nchunks = reinterpret_cast<const int32_t *>(base + o_ln);
+    pl.lchunk_rec = reinterpret_cast<const int32_t *>(base + o_lcr);
+    pl.lchunk_idx = reinterpret_cast<const int32_t *>(base + o_lci);
     h->ws_need = carve(pl, nullptr, nullptr);
     h->planned = true;
     if (workspace_bytes_out) *workspace_bytes_out = h->ws_need;

@@ -11,6 +11,8 @@ namespace vbx {
 
 constexpr int kLTile = 64;    // frames per CTA tile of the log-likelihood kernel
 constexpr int kMTile = 512;   // frames per CTA tile of the M-step accumulation / mma log-likelihood kernels
+constexpr int kLongT = 4096;   // recordings at least this long take the chunked-scan forward-backward
+constexpr int kChunk = 256;    // frames per chunk of that scan
 constexpr int kMaxR = 128;
 constexpr int kMaxS = 64;
 
@@ -27,6 +29,13 @@ struct Plan {
     const int32_t *mtile_rec = nullptr; // [n_mtiles]
     const int64_t *mtile_f0 = nullptr;  // [n_mtiles]
     const int32_t *mtile_begin = nullptr; // [n_rec+1] first M-tile of each recording
+    // long recordings (T >= kLongT): chunked-scan forward-backward (vbx_long_kernels.cu)
+    int32_t n_lrec = 0, n_lchunks = 0;
+    const int32_t *lrec_list = nullptr;    // [n_lrec]   recording ids
+    const int32_t *lrec_first = nullptr;   // [n_rec]    first chunk index of the recording (long ones only)
+    const int32_t *lrec_nchunks = nullptr; // [n_rec]    number of chunks, 0 for short recordings
+    const int32_t *lchunk_rec = nullptr;   // [n_lchunks]
+    const int32_t *lchunk_idx = nullptr;   // [n_lchunks] chunk number inside its recording
 };
 
 // Caller-provided workspace, carved by the handle.
@@ -40,12 +49,16 @@ struct Workspace {
     float *Afrag_lo = nullptr; //   (NT = max(1,S/8) n-tiles, KS = ceil(R/8) k-steps; see vbx_mma_kernels.cu)
     float *bias = nullptr;     // [n_rec,S]    Fa * 0.5 * sum_r (invL + alpha^2) Phi_r ; +inf for dead columns
     float *occ = nullptr;      // [n_rec,S]    N_s = sum_t gamma
-    double *reg = nullptr;     // [n_rec]      0.5 Fb sum (log invL - invL - alpha^2 + 1)
+    double *regp = nullptr;    // [n_rec,S]    per speaker: sum_r (log invL - invL - alpha^2 + 1)
     double *gsum = nullptr;    // [n_rec]      sum_t G_t
     double *gpart = nullptr;   // [n_mtiles]
     double *prev_elbo = nullptr; // [n_rec]
     int32_t *active = nullptr; // [n_rec]
     float *scratch = nullptr;  // [2*kMaxS] write sink for warp lanes that own no recording
+    // chunked scan of long recordings: per (chunk, basis) operators and per-chunk boundary vectors / partial sums
+    float *fa_u = nullptr, *fa_lam = nullptr, *fa_exp = nullptr, *astart = nullptr;   // [LC,S,S], [LC,S] mantissa, [LC,S] exponent, [LC,S]
+    float *bb_v = nullptr, *bb_mu = nullptr, *bb_exp = nullptr, *beta = nullptr;      // same shapes, backward sweep
+    float *occp = nullptr, *entp = nullptr;                        // [n_lchunks,S]
 };
 
 struct RunParams {
@@ -53,6 +66,81 @@ struct RunParams {
     double dFa, dFb, dFaFb, epsilon;
     int32_t max_iters;
 };
+
+#ifdef __CUDACC__
+// small vector load/store helpers shared by the kernel translation units
+template <int N>
+struct Vec {
+    float v[N];
+};
+template <int N>
+__device__ __forceinline__ Vec<N> ld_vec(const float *p);
+template <>
+__device__ __forceinline__ Vec<1> ld_vec<1>(const float *p) {
+    Vec<1> r;
+    r.v[0] = *p;
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<2> ld_vec<2>(const float *p) {
+    float2 t = *reinterpret_cast<const float2 *>(p);
+    Vec<2> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<4> ld_vec<4>(const float *p) {
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    Vec<4> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    r.v[2] = t.z;
+    r.v[3] = t.w;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Vec<N> ldg_vec(const float *p);
+template <>
+__device__ __forceinline__ Vec<1> ldg_vec<1>(const float *p) {
+    Vec<1> r;
+    r.v[0] = __ldg(p);
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<2> ldg_vec<2>(const float *p) {
+    float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    Vec<2> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<4> ldg_vec<4>(const float *p) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    Vec<4> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    r.v[2] = t.z;
+    r.v[3] = t.w;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ void st_vec(float *p, const float *v);
+template <>
+__device__ __forceinline__ void st_vec<1>(float *p, const float *v) {
+    *p = v[0];
+}
+template <>
+__device__ __forceinline__ void st_vec<2>(float *p, const float *v) {
+    *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+}
+template <>
+__device__ __forceinline__ void st_vec<4>(float *p, const float *v) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+#endif  // __CUDACC__
 
 // launchers (vbx_kernels.cu); each returns the number of kernels launched or -1 on launch error
 int launch_prepare_scale(const Plan &pl, const Workspace &ws, const float *fea, const float *Phi, float *rho,
@@ -69,6 +157,9 @@ int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStr
 int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
                             int spl, cudaStream_t st);
+// chunked-scan forward-backward for long recordings (vbx_long_kernels.cu)
+int launch_forward_backward_long(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
+                                 const int32_t *n_states, cudaStream_t st);
 // tensor-core (mma.sync 3xTF32) versions of the two in-loop contractions (vbx_mma_kernels.cu)
 int launch_mstep_mma(const Plan &pl, const Workspace &ws, const float *rho, const float *gamma, cudaStream_t st);
 int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st);

@@ -46,77 +46,6 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-template <int N>
-struct Vec {
-    float v[N];
-};
-template <int N>
-__device__ __forceinline__ Vec<N> ld_vec(const float *p);
-template <>
-__device__ __forceinline__ Vec<1> ld_vec<1>(const float *p) {
-    Vec<1> r;
-    r.v[0] = *p;
-    return r;
-}
-template <>
-__device__ __forceinline__ Vec<2> ld_vec<2>(const float *p) {
-    float2 t = *reinterpret_cast<const float2 *>(p);
-    Vec<2> r;
-    r.v[0] = t.x;
-    r.v[1] = t.y;
-    return r;
-}
-template <>
-__device__ __forceinline__ Vec<4> ld_vec<4>(const float *p) {
-    float4 t = *reinterpret_cast<const float4 *>(p);
-    Vec<4> r;
-    r.v[0] = t.x;
-    r.v[1] = t.y;
-    r.v[2] = t.z;
-    r.v[3] = t.w;
-    return r;
-}
-template <int N>
-__device__ __forceinline__ Vec<N> ldg_vec(const float *p);
-template <>
-__device__ __forceinline__ Vec<1> ldg_vec<1>(const float *p) {
-    Vec<1> r;
-    r.v[0] = __ldg(p);
-    return r;
-}
-template <>
-__device__ __forceinline__ Vec<2> ldg_vec<2>(const float *p) {
-    float2 t = __ldg(reinterpret_cast<const float2 *>(p));
-    Vec<2> r;
-    r.v[0] = t.x;
-    r.v[1] = t.y;
-    return r;
-}
-template <>
-__device__ __forceinline__ Vec<4> ldg_vec<4>(const float *p) {
-    float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-    Vec<4> r;
-    r.v[0] = t.x;
-    r.v[1] = t.y;
-    r.v[2] = t.z;
-    r.v[3] = t.w;
-    return r;
-}
-template <int N>
-__device__ __forceinline__ void st_vec(float *p, const float *v);
-template <>
-__device__ __forceinline__ void st_vec<1>(float *p, const float *v) {
-    *p = v[0];
-}
-template <>
-__device__ __forceinline__ void st_vec<2>(float *p, const float *v) {
-    *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
-}
-template <>
-__device__ __forceinline__ void st_vec<4>(float *p, const float *v) {
-    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-
 // ------------------------------------------------------------------------------------------------
 // prepare: rho = fea * sqrt(Phi), G partial sums per M-tile          VBx/VBx.py:87-89
 // MODE 0: in = fea, writes rho, ||x||^2 from fea.   MODE 1: in = rho (read only), ||x||^2 = sum rho^2/Phi.
@@ -417,91 +346,94 @@ int launch_mstep_partial(const Plan &pl, const Workspace &ws, const float *rho, 
 
 // ------------------------------------------------------------------------------------------------
 // speaker model: invL, alpha (eqs 17,16; VBx/VBx.py:95-96), the per-speaker bias of eq. (23)
-// (VBx/VBx.py:97) and the ELBO regulariser of eq. (25) (VBx/VBx.py:100).  One CTA per recording,
-// thread = r.  Sums over tiles run in tile order in float64 (deterministic).
+// (VBx/VBx.py:97) and the per-speaker parts of the ELBO regulariser of eq. (25) (VBx/VBx.py:100).  One CTA per
+// (recording, speaker), thread = r.  Sums over tiles run in tile order in float64 (deterministic).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) speaker_model_kernel(Plan pl, Workspace ws, RunParams rp,
                                                             const float *__restrict__ Phi,
                                                             const int32_t *__restrict__ n_states, float *alpha_io,
                                                             float *invL_io, int from_given) {
-    const int rec = blockIdx.x;
-    if (!ws.active[rec]) return;
+    // one CTA per (recording, speaker): thread = r
     const int S = pl.S, R = pl.R;
+    const int NT = S > 8 ? S / 8 : 1, S8 = 8 * NT;
+    const int rec = blockIdx.x / S8, s = blockIdx.x % S8;
+    if (!ws.active[rec]) return;
     const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
     const bool live = r < R;
     const int ns = n_states ? n_states[rec] : S;
     const float phi = live ? Phi[r] : 0.f;
     const int t_lo = pl.mtile_begin[rec], t_hi = pl.mtile_begin[rec + 1];
-    __shared__ double cpart[4][kMaxS];
-    __shared__ double rpart[4];
     // mma fragment-major copy of Fa*alpha, split into TF32 hi/lo (consumed by loglik_mma_kernel)
-    const int NT = S > 8 ? S / 8 : 1, KS = (R + 7) >> 3, KQ = 2 * KS;
+    const int KS = (R + 7) >> 3, KQ = 2 * KS;
     const bool fragcol = r < 8 * KS;
     // column r -> (k-step fj, quad lane fq, half fe); R = 128 uses the coalesced permutation of loglik_mma_kernel
     const int fq = R == 128 ? (r >> 2) & 3 : r / KQ;
     const int fj = R == 128 ? 2 * (r >> 4) + ((r >> 1) & 1) : (r - fq * KQ) >> 1;
     const int fe = r & 1;
-    double regacc = 0.0;
-    for (int s = 0; s < 8 * NT; ++s) {
-        const int64_t o = ((int64_t)rec * S + s) * R + r;
-        const int64_t fo = (((int64_t)rec * NT + (s >> 3)) * KS + fj) * 64 + ((s & 7) * 4 + fq) * 2 + fe;
-        if (s >= ns) {  // dead (or padding) column: never wins, never contributes
-            if (live && s < S) {
-                ws.A[o] = 0.f;
-                if (alpha_io) alpha_io[o] = 0.f;
-                if (invL_io) invL_io[o] = 0.f;
-            }
-            if (fragcol) {
-                ws.Afrag_hi[fo] = 0.f;
-                ws.Afrag_lo[fo] = 0.f;
-            }
-            continue;
-        }
-        float invL = 1.f, alpha = 0.f, Av = 0.f;
-        double c = 0.0;
-        if (live) {
-            if (from_given) {
-                alpha = alpha_io[o];
-                invL = invL_io[o];
-            } else {
-                double gr = 0.0;
-                for (int t = t_lo; t < t_hi; ++t) gr += (double)ws.partial[((int64_t)t * S + s) * R + r];
-                const float Ns = ws.occ[(int64_t)rec * S + s];
-                invL = 1.f / (1.f + rp.FaFb * Ns * phi);
-                alpha = (float)((double)(rp.FaFb * invL) * gr);
-                if (alpha_io) alpha_io[o] = alpha;
-                if (invL_io) invL_io[o] = invL;
-            }
-            Av = rp.Fa * alpha;
-            ws.A[o] = Av;
-            const float a2 = alpha * alpha;
-            regacc += (double)(logf(invL) - invL - a2 + 1.f);
-            c = (double)((invL + a2) * phi);
+    const int64_t o = ((int64_t)rec * S + s) * R + r;
+    const int64_t fo = (((int64_t)rec * NT + (s >> 3)) * KS + fj) * 64 + ((s & 7) * 4 + fq) * 2 + fe;
+    if (s >= ns) {  // dead (or padding) column: never wins, never contributes
+        if (live && s < S) {
+            ws.A[o] = 0.f;
+            if (alpha_io) alpha_io[o] = 0.f;
+            if (invL_io) invL_io[o] = 0.f;
         }
         if (fragcol) {
-            const float hi = __uint_as_float(__float_as_uint(Av) & 0xffffe000u);
-            ws.Afrag_hi[fo] = hi;
-            ws.Afrag_lo[fo] = Av - hi;
+            ws.Afrag_hi[fo] = 0.f;
+            ws.Afrag_lo[fo] = 0.f;
         }
-        c = warp_sum_d(c);
-        if (lane == 0) cpart[warp][s] = c;
+        if (r == 0 && s < S) {
+            ws.bias[(int64_t)rec * S + s] = CUDART_INF_F;
+            ws.regp[(int64_t)rec * S + s] = 0.0;
+        }
+        return;
     }
-    regacc = warp_sum_d(regacc);
-    if (lane == 0) rpart[warp] = regacc;
+    float invL = 1.f, alpha = 0.f, Av = 0.f;
+    double c = 0.0, reg = 0.0;
+    if (live) {
+        if (from_given) {
+            alpha = alpha_io[o];
+            invL = invL_io[o];
+        } else {
+            double gr = 0.0;
+            for (int t = t_lo; t < t_hi; ++t) gr += (double)ws.partial[((int64_t)t * S + s) * R + r];
+            const float Ns = ws.occ[(int64_t)rec * S + s];
+            invL = 1.f / (1.f + rp.FaFb * Ns * phi);
+            alpha = (float)((double)(rp.FaFb * invL) * gr);
+            if (alpha_io) alpha_io[o] = alpha;
+            if (invL_io) invL_io[o] = invL;
+        }
+        Av = rp.Fa * alpha;
+        ws.A[o] = Av;
+        const float a2 = alpha * alpha;
+        reg = (double)(logf(invL) - invL - a2 + 1.f);
+        c = (double)((invL + a2) * phi);
+    }
+    if (fragcol) {
+        const float hi = __uint_as_float(__float_as_uint(Av) & 0xffffe000u);
+        ws.Afrag_hi[fo] = hi;
+        ws.Afrag_lo[fo] = Av - hi;
+    }
+    __shared__ double cpart[4], rpart[4];
+    c = warp_sum_d(c);
+    reg = warp_sum_d(reg);
+    if (lane == 0) {
+        cpart[warp] = c;
+        rpart[warp] = reg;
+    }
     __syncthreads();
-    if (r < S) {
-        float bias = CUDART_INF_F;
-        if (r < ns) bias = (float)(rp.dFa * 0.5 * (cpart[0][r] + cpart[1][r] + cpart[2][r] + cpart[3][r]));
-        ws.bias[(int64_t)rec * S + r] = bias;
+    if (r == 0) {
+        ws.bias[(int64_t)rec * S + s] = (float)(rp.dFa * 0.5 * ((cpart[0] + cpart[1]) + (cpart[2] + cpart[3])));
+        ws.regp[(int64_t)rec * S + s] = (rpart[0] + rpart[1]) + (rpart[2] + rpart[3]);
     }
-    if (r == 0) ws.reg[rec] = 0.5 * rp.dFb * (rpart[0] + rpart[1] + rpart[2] + rpart[3]);
 }
 
 int launch_speaker_model(const Plan &pl, const Workspace &ws, const RunParams &rp, const float *Phi,
                          const int32_t *n_states, float *alpha_io, float *invL_io, bool from_given,
                          cudaStream_t st) {
     if (pl.n_rec == 0) return 0;
-    speaker_model_kernel<<<pl.n_rec, 128, 0, st>>>(pl, ws, rp, Phi, n_states, alpha_io, invL_io, from_given ? 1 : 0);
+    const int S8 = pl.S > 8 ? pl.S : 8;
+    speaker_model_kernel<<<pl.n_rec * S8, 128, 0, st>>>(pl, ws, rp, Phi, n_states, alpha_io, invL_io, from_given ? 1 : 0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -648,7 +580,8 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
     const int slot = warp_global * RPW + g;
     int rec = -1;
     if (slot < pl.n_rec) rec = pl.order[slot];
-    const bool live = rec >= 0 && ws.active[rec] != 0;
+    // long recordings are handled by the chunked scan (vbx_long_kernels.cu)
+    const bool live = rec >= 0 && ws.active[rec] != 0 && pl.lrec_nchunks[rec] == 0;
     int64_t f0 = 0;
     int T = 0;
     if (live) {
@@ -868,24 +801,29 @@ static int launch_fb_t(const Plan &pl, const Workspace &ws, const RunParams &rp,
 }
 
 // ------------------------------------------------------------------------------------------------
-// ELBO + stop test: one warp per recording                         VBx/VBx.py:100,105,122-125,173
+// ELBO + stop test: one CTA per recording                           VBx/VBx.py:100,105,122-125,173
 //   tll = sum_t (log sigma_t + rowmax_t) + Fa * sum_t G_t ;  ELBO = tll + reg
 // float64, fixed summation order (lane-strided partial sums, xor tree) => deterministic.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) elbo_kernel(Plan pl, Workspace ws, RunParams rp, double *Li, int32_t *n_iters,
                                                    int32_t *flags, int iter) {
-    const int rec = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (rec >= pl.n_rec || !ws.active[rec]) return;
+    const int rec = blockIdx.x;
+    if (!ws.active[rec]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t f0 = pl.offsets[rec];
     const int T = (int)(pl.offsets[rec + 1] - f0);
     const float *rs = ws.rsigma + f0;
     const float *mx = ws.rowmax + f0;
     double acc = 0.0;
-    for (int t = lane; t < T; t += 32) acc += (double)mx[t] - log((double)rs[t]);
+    for (int t = tid; t < T; t += 128) acc += (double)mx[t] - log((double)rs[t]);
     acc = warp_sum_d(acc);
-    if (lane == 0) {
-        const double elbo = acc + rp.dFa * ws.gsum[rec] + ws.reg[rec];
+    __shared__ double part[4];
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double reg = 0.0;                         // eq. (25) regulariser: per-speaker parts in speaker order
+        for (int s = 0; s < pl.S; ++s) reg += ws.regp[(int64_t)rec * pl.S + s];
+        const double elbo = (part[0] + part[1]) + (part[2] + part[3]) + rp.dFa * ws.gsum[rec] + 0.5 * rp.dFb * reg;
         Li[(int64_t)rec * rp.max_iters + iter] = elbo;
         n_iters[rec] = iter + 1;
         int fl = flags[rec];
@@ -942,8 +880,10 @@ int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams
     }
 #undef VBX_FB
     if (rc < 0) return rc;
-    elbo_kernel<<<(pl.n_rec + 3) / 4, 128, 0, st>>>(pl, ws, rp, Li, n_iters, flags, iter);
-    return cudaGetLastError() == cudaSuccess ? rc + 1 : -1;
+    const int rl = launch_forward_backward_long(pl, ws, rp, gamma, pi, n_states, st);
+    if (rl < 0) return rl;
+    elbo_kernel<<<pl.n_rec, 128, 0, st>>>(pl, ws, rp, Li, n_iters, flags, iter);
+    return cudaGetLastError() == cudaSuccess ? rc + rl + 1 : -1;
 }
 
 }  // namespace vbx
