@@ -347,84 +347,95 @@ int launch_mstep_partial(const Plan &pl, const Workspace &ws, const float *rho, 
 // ------------------------------------------------------------------------------------------------
 // speaker model: invL, alpha (eqs 17,16; VBx/VBx.py:95-96), the per-speaker bias of eq. (23)
 // (VBx/VBx.py:97) and the per-speaker parts of the ELBO regulariser of eq. (25) (VBx/VBx.py:100).  One CTA per
-// (recording, speaker), thread = r.  Sums over tiles run in tile order in float64 (deterministic).
+// recording, four 128-thread warp-groups each taking every 4th speaker, thread = r.  Sums over tiles run in tile order in float64 (deterministic).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) speaker_model_kernel(Plan pl, Workspace ws, RunParams rp,
+template <int S8, bool R128>
+__global__ void __launch_bounds__(512) speaker_model_kernel(Plan pl, Workspace ws, RunParams rp,
                                                             const float *__restrict__ Phi,
                                                             const int32_t *__restrict__ n_states, float *alpha_io,
                                                             float *invL_io, int from_given) {
-    // one CTA per (recording, speaker): thread = r
+    // one CTA per recording; four 128-thread warp-groups, each takes every 4th speaker, thread = r
     const int S = pl.S, R = pl.R;
-    const int NT = S > 8 ? S / 8 : 1, S8 = 8 * NT;
-    const int rec = blockIdx.x / S8, s = blockIdx.x % S8;
-    if (!ws.active[rec]) return;
-    const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
+    constexpr int NT = S8 / 8, NSP = S8 / 4;   // speakers per warp-group
+    const int rec = blockIdx.x;
+    if (!ws.active[rec]) return;            // CTA-uniform
+    const int wg = threadIdx.x >> 7;
+    const int r = threadIdx.x & 127, warp = r >> 5, lane = r & 31;
     const bool live = r < R;
     const int ns = n_states ? n_states[rec] : S;
     const float phi = live ? Phi[r] : 0.f;
     const int t_lo = pl.mtile_begin[rec], t_hi = pl.mtile_begin[rec + 1];
-    // mma fragment-major copy of Fa*alpha, split into TF32 hi/lo (consumed by loglik_mma_kernel)
-    const int KS = (R + 7) >> 3, KQ = 2 * KS;
-    const bool fragcol = r < 8 * KS;
-    // column r -> (k-step fj, quad lane fq, half fe); R = 128 uses the coalesced permutation of loglik_mma_kernel
-    const int fq = R == 128 ? (r >> 2) & 3 : r / KQ;
-    const int fj = R == 128 ? 2 * (r >> 4) + ((r >> 1) & 1) : (r - fq * KQ) >> 1;
-    const int fe = r & 1;
-    const int64_t o = ((int64_t)rec * S + s) * R + r;
-    const int64_t fo = (((int64_t)rec * NT + (s >> 3)) * KS + fj) * 64 + ((s & 7) * 4 + fq) * 2 + fe;
-    if (s >= ns) {  // dead (or padding) column: never wins, never contributes
+    extern __shared__ float sAv[];                       // [S8][kMaxR] Fa*alpha, staged for the coalesced fragment writes
+    __shared__ double cpart[kMaxS][4], rpart[kMaxS][4];
+    // all tile sums of this thread's speakers first (independent loads in flight), then the per-speaker math
+    double grs[NSP];
+#pragma unroll
+    for (int k = 0; k < NSP; ++k) {
+        const int s = wg + 4 * k;
+        double gr = 0.0;
+        if (live && s < ns && !from_given)
+            for (int t = t_lo; t < t_hi; ++t) gr += (double)__ldg(ws.partial + ((int64_t)t * S + s) * R + r);
+        grs[k] = gr;
+    }
+#pragma unroll
+    for (int k = 0; k < NSP; ++k) {
+        const int s = wg + 4 * k;
+        const int64_t o = ((int64_t)rec * S + s) * R + r;
+        const bool dead = s >= ns;   // dead (or padding) column: never wins, never contributes
+        float invL = 1.f, alpha = 0.f, Av = 0.f;
+        float c = 0.f, reg = 0.f;
+        if (live && !dead) {
+            if (from_given) {
+                alpha = alpha_io[o];
+                invL = invL_io[o];
+            } else {
+                const double gr = grs[k];
+                const float Ns = ws.occ[(int64_t)rec * S + s];
+                invL = 1.f / (1.f + rp.FaFb * Ns * phi);
+                alpha = (float)((double)(rp.FaFb * invL) * gr);
+            }
+            Av = rp.Fa * alpha;
+            const float a2 = alpha * alpha;
+            reg = logf(invL) - invL - a2 + 1.f;
+            c = (invL + a2) * phi;
+        }
         if (live && s < S) {
-            ws.A[o] = 0.f;
-            if (alpha_io) alpha_io[o] = 0.f;
-            if (invL_io) invL_io[o] = 0.f;
+            ws.A[o] = Av;
+            if (!from_given || dead) {
+                if (alpha_io) alpha_io[o] = dead ? 0.f : alpha;
+                if (invL_io) invL_io[o] = dead ? 0.f : invL;
+            }
         }
-        if (fragcol) {
-            ws.Afrag_hi[fo] = 0.f;
-            ws.Afrag_lo[fo] = 0.f;
+        sAv[s * kMaxR + r] = Av;                          // columns >= R hold 0
+        c = group_sum<32>(c);                             // 32 terms in float, the rest in float64
+        reg = group_sum<32>(reg);
+        if (lane == 0) {
+            cpart[s][warp] = (double)c;
+            rpart[s][warp] = (double)reg;
         }
-        if (r == 0 && s < S) {
-            ws.bias[(int64_t)rec * S + s] = CUDART_INF_F;
-            ws.regp[(int64_t)rec * S + s] = 0.0;
-        }
-        return;
-    }
-    float invL = 1.f, alpha = 0.f, Av = 0.f;
-    double c = 0.0, reg = 0.0;
-    if (live) {
-        if (from_given) {
-            alpha = alpha_io[o];
-            invL = invL_io[o];
-        } else {
-            double gr = 0.0;
-            for (int t = t_lo; t < t_hi; ++t) gr += (double)ws.partial[((int64_t)t * S + s) * R + r];
-            const float Ns = ws.occ[(int64_t)rec * S + s];
-            invL = 1.f / (1.f + rp.FaFb * Ns * phi);
-            alpha = (float)((double)(rp.FaFb * invL) * gr);
-            if (alpha_io) alpha_io[o] = alpha;
-            if (invL_io) invL_io[o] = invL;
-        }
-        Av = rp.Fa * alpha;
-        ws.A[o] = Av;
-        const float a2 = alpha * alpha;
-        reg = (double)(logf(invL) - invL - a2 + 1.f);
-        c = (double)((invL + a2) * phi);
-    }
-    if (fragcol) {
-        const float hi = __uint_as_float(__float_as_uint(Av) & 0xffffe000u);
-        ws.Afrag_hi[fo] = hi;
-        ws.Afrag_lo[fo] = Av - hi;
-    }
-    __shared__ double cpart[4], rpart[4];
-    c = warp_sum_d(c);
-    reg = warp_sum_d(reg);
-    if (lane == 0) {
-        cpart[warp] = c;
-        rpart[warp] = reg;
     }
     __syncthreads();
-    if (r == 0) {
-        ws.bias[(int64_t)rec * S + s] = (float)(rp.dFa * 0.5 * ((cpart[0] + cpart[1]) + (cpart[2] + cpart[3])));
-        ws.regp[(int64_t)rec * S + s] = (rpart[0] + rpart[1]) + (rpart[2] + rpart[3]);
+    if (threadIdx.x < S) {
+        const int s = threadIdx.x;
+        const bool dead = s >= ns;
+        ws.bias[(int64_t)rec * S + s] =
+            dead ? CUDART_INF_F : (float)(rp.dFa * 0.5 * ((cpart[s][0] + cpart[s][1]) + (cpart[s][2] + cpart[s][3])));
+        ws.regp[(int64_t)rec * S + s] = dead ? 0.0 : (rpart[s][0] + rpart[s][1]) + (rpart[s][2] + rpart[s][3]);
+    }
+    // mma fragment-major copy of Fa*alpha, split into TF32 hi/lo (consumed by loglik_mma_kernel): linear, coalesced
+    // writes; element q = ((i*KS + j)*32 + lane)*2 + e  <->  state 8i + lane/4, column col(j, lane%4, e)
+    const int KS = R128 ? 16 : (R + 7) >> 3, KQ = 2 * KS;
+    float *fh = ws.Afrag_hi + (int64_t)rec * NT * KS * 64, *fl = ws.Afrag_lo + (int64_t)rec * NT * KS * 64;
+    for (int q = threadIdx.x; q < NT * KS * 64; q += 512) {
+        const int e = q & 1, ln = (q >> 1) & 31, ij = q >> 6;
+        const int j = R128 ? (ij & 15) : ij % KS, i = R128 ? (ij >> 4) : ij / KS;
+        const int st = 8 * i + (ln >> 2), fq = ln & 3;
+        // R = 128 uses the coalesced column permutation of loglik_mma_kernel, other R the plain one
+        const int col = R128 ? 16 * (j >> 1) + 4 * fq + 2 * (j & 1) + e : KQ * fq + 2 * j + e;
+        const float Av = col < kMaxR ? sAv[st * kMaxR + col] : 0.f;
+        const float hi = __uint_as_float(__float_as_uint(Av) & 0xffffe000u);
+        fh[q] = hi;
+        fl[q] = Av - hi;
     }
 }
 
@@ -433,7 +444,25 @@ int launch_speaker_model(const Plan &pl, const Workspace &ws, const RunParams &r
                          cudaStream_t st) {
     if (pl.n_rec == 0) return 0;
     const int S8 = pl.S > 8 ? pl.S : 8;
-    speaker_model_kernel<<<pl.n_rec * S8, 128, 0, st>>>(pl, ws, rp, Phi, n_states, alpha_io, invL_io, from_given ? 1 : 0);
+    const size_t smem = (size_t)S8 * kMaxR * sizeof(float);
+    const int fg = from_given ? 1 : 0;
+#define VBX_SM(S8_, R_) speaker_model_kernel<S8_, R_><<<pl.n_rec, 512, smem, st>>>(pl, ws, rp, Phi, n_states, alpha_io, invL_io, fg)
+    if (pl.R == 128) {
+        switch (S8) {
+            case 8: VBX_SM(8, true); break;
+            case 16: VBX_SM(16, true); break;
+            case 32: VBX_SM(32, true); break;
+            default: VBX_SM(64, true); break;
+        }
+    } else {
+        switch (S8) {
+            case 8: VBX_SM(8, false); break;
+            case 16: VBX_SM(16, false); break;
+            case 32: VBX_SM(32, false); break;
+            default: VBX_SM(64, false); break;
+        }
+    }
+#undef VBX_SM
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
