@@ -450,3 +450,62 @@ def test_c_abi_argument_errors():
     assert lib.vbx_plan(h, po, 1, 128, 16, ctypes.byref(need)) == 0 and need.value > 0
     assert lib.vbx_bind_workspace(h, None, 0) == -3
     assert lib.vbx_destroy(h) == 0
+
+
+def test_float64_mode_ragged_batch_vs_oracle():
+    """vbx_run_f64 on a ragged multi-recording batch with per-recording state counts."""
+    from vbx_b200.batch import VbxBatch, run_f64
+    S = 10
+    lens, d = ragged_batch(7, S, seed=61, tmax=300)
+    ns = np.array([10, 3, 10, 7, 1, 10, 5], dtype=np.int32)
+    g0 = d['gamma0'].astype(np.float64)
+    for b, (lo, hi) in enumerate(zip(d['offsets'][:-1], d['offsets'][1:])):
+        g0[lo:hi, ns[b]:] = 0
+        g0[lo:hi] /= g0[lo:hi].sum(1, keepdims=True)
+    pi0 = np.zeros((len(lens), S))
+    for b in range(len(lens)):
+        pi0[b, :ns[b]] = 1.0 / ns[b]
+    ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], g0, pi0, 0.4, 17.0, 0.4, 9, 1e-3, n_states=ns)
+    vb = VbxBatch(lens, 128, ns, device=dev(), allocate=False)
+    g = torch.zeros((int(lens.sum()), vb.S), dtype=torch.float64, device=dev())
+    g[:, :S] = cuda(g0, torch.float64)
+    p = torch.zeros((len(lens), vb.S), dtype=torch.float64, device=dev())
+    p[:, :S] = cuda(pi0, torch.float64)
+    out = run_f64(vb, cuda(d['fea'], torch.float64), cuda(d['Phi'], torch.float64), g, p, Fa=0.4, Fb=17.0, loopProb=0.4,
+                  maxIters=9, epsilon=1e-3)
+    assert np.array_equal(out['n_iters'].cpu().numpy(), ref['n_iters'])
+    np.testing.assert_allclose(g[:, :S].cpu().numpy(), ref['gamma'], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(p[:, :S].cpu().numpy(), ref['pi'], rtol=0, atol=1e-9)
+    Li = out['Li'].cpu().numpy()
+    assert np.array_equal(np.isnan(Li), np.isnan(ref['Li']))
+    np.testing.assert_allclose(np.nan_to_num(Li), np.nan_to_num(ref['Li']), rtol=1e-10)
+    vb.close()
+
+
+def test_host_pipeline_equals_resident_path():
+    """The host-buffer API (pinned host X / gamma0 in, gamma / pi / Li out, chunked over streams) gives bit-identical
+    results to the device-resident calls, including per-recording state padding."""
+    from vbx_b200.batch import VbxBatch
+    from vbx_b200.host_pipeline import HostPipeline
+    lens = np.array([700, 20, 333, 1, 512, 90, 1500, 64])
+    S = 6
+    d = synth.make_batch(lens, R=128, S=S, seed=41, D=256, dtype=np.float32)
+    kw = dict(Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=5, epsilon=-np.inf)
+    vb = VbxBatch(lens, 128, S, device=dev())
+    vb.prepare_project(cuda(d['X']), cuda(d['V']), cuda(d['Phi']))
+    g = torch.zeros((int(lens.sum()), vb.S), device=dev())
+    g[:, :S] = cuda(d['gamma0'])
+    p = torch.zeros((len(lens), vb.S), device=dev())
+    p[:, :S] = 1.0 / S
+    res = vb.run(g, p, **kw)
+    torch.cuda.synchronize()
+    hp = HostPipeline(lens, 256, 128, S, device=dev(), n_chunks=3)
+    Xh = torch.from_numpy(d['X']).pin_memory()
+    Gh = torch.from_numpy(d['gamma0']).pin_memory()
+    out = hp.run(Xh, cuda(d['V']), cuda(d['Phi']), Gh, **kw)
+    assert hp.n_chunks == 3
+    assert torch.equal(out['gamma'], g[:, :S].cpu())
+    assert torch.equal(out['pi'], p[:, :S].cpu())
+    assert torch.equal(out['Li'], res['Li'].cpu())
+    assert hp.h2d_bytes == int(lens.sum()) * (256 + S) * 4
+    vb.close()
