@@ -509,3 +509,22 @@ def test_host_pipeline_equals_resident_path():
     assert torch.equal(out['Li'], res['Li'].cpu())
     assert hp.h2d_bytes == int(lens.sum()) * (256 + S) * 4
     vb.close()
+
+
+def test_dropin_pads_odd_feature_dims():
+    """lda_dim values that are not a multiple of 4 (VBx/vbhmm.py --lda-dim is free): zero-padded on the host."""
+    from vbx_b200 import VBx
+    from oracle import vbx_oracle as po
+    rng = np.random.default_rng(12)
+    T, R, S = 150, 50, 5
+    Phi = synth.plda_phi(R)
+    fea, _ = synth.make_recording(T, R, Phi, rng, n_spk=3)
+    g0 = synth.dirichlet_rows(T, S, rng)
+    g, p, L, a, il = VBx(fea, Phi, loopProb=0.8, Fa=0.4, Fb=17.0, pi=S, gamma=g0, maxIters=8, epsilon=1e-4, return_model=True)
+    gr, pr, Lr, ar, ilr = po.vbx_oracle(fea, Phi, loopProb=0.8, Fa=0.4, Fb=17.0, pi=S, gamma=g0, maxIters=8, epsilon=1e-4,
+                                        return_model=True)
+    assert len(L) == len(Lr) and a.shape == (S, R) and il.shape == (S, R)
+    np.testing.assert_allclose(g, gr, atol=1e-7)
+    np.testing.assert_allclose([l[0] for l in L], [l[0] for l in Lr], rtol=1e-9)
+    np.testing.assert_allclose(a, ar, atol=1e-7)
+    np.testing.assert_allclose(il, ilr, atol=1e-9)

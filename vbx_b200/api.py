@@ -50,6 +50,22 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
     X = np.asarray(X)
     Phi = np.asarray(Phi)
     T, D = X.shape                                    # VBx/VBx.py:74
+    if D % 4 != 0 and D < 128:
+        # The kernels want a feature dimension that is a multiple of 4.  Zero features with zero across-class
+        # variance are inert: invL = 1, alpha = 0, no bias, no regulariser term; only the constant D*log(2*pi) of G
+        # (VBx/VBx.py:87) depends on D, which is put back into the ELBO trace below.
+        pad = 4 - D % 4
+        res = VBx(np.concatenate([X, np.zeros((T, pad), dtype=X.dtype)], axis=1),
+                  np.concatenate([Phi, np.zeros(pad, dtype=Phi.dtype)]), loopProb=loopProb, Fa=Fa, Fb=Fb, pi=pi, gamma=gamma,
+                  maxIters=maxIters, epsilon=epsilon, alphaQInit=alphaQInit, ref=ref, plot=plot, return_model=return_model,
+                  alpha=None if alpha is None else np.concatenate([alpha, np.zeros((alpha.shape[0], pad))], axis=1),
+                  invL=None if invL is None else np.concatenate([invL, np.ones((invL.shape[0], pad))], axis=1))
+        shift = 0.5 * Fa * T * pad * np.log(2 * np.pi)
+        Li = [[l[0] + shift] + l[1:] for l in res[2]]
+        out = (res[0], res[1], Li)
+        if return_model:
+            out = out + (res[3][:, :D], res[4][:, :D])
+        return out
     if type(pi) is int:                               # VBx/VBx.py:76-77 (np.int64 is *not* accepted there either)
         pi = np.ones(pi) / pi
     S = len(pi)
