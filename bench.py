@@ -270,6 +270,9 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--fb-spl', type=int, default=0)
     ap.add_argument('--projection', type=int, default=0)
+    ap.add_argument('--front', default='project', choices=['project', 'xvectors'],
+                    help="what feeds the EM loop: 'project' = rho = X.V (the headline definition, SURVEY 8d); 'xvectors' = the "
+                         "real-data chain vbx_prepare_xvectors (x-vector transform + PLDA projection, two tcgen05 passes)")
     ap.add_argument('--extra', default='', help='comma separated extra workloads to time (kernel-only) in the same run')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -321,8 +324,20 @@ def main():
             flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
         vb.n_states = None if w['S'] == S else torch.full((len(lengths),), w['S'], dtype=torch.int32, device=device)
 
+        model = None
+        if args.front == 'xvectors':       # synthetic model with the shapes of VBx/models/ResNet101_16kHz
+            gen = torch.Generator(device='cpu').manual_seed(5)
+            rnd = lambda *shape: torch.randn(*shape, generator=gen)
+            q, _ = torch.linalg.qr(rnd(R_DIM, R_DIM))
+            model = [t.to(device).contiguous() for t in (
+                rnd(D_RAW) * 0.5, rnd(D_RAW, R_DIM) / D_RAW ** 0.5, rnd(R_DIM) * 0.05, rnd(R_DIM) * 0.02,
+                q * (2.0 + 18.0 * torch.rand(R_DIM, generator=gen))[:, None])] + [data['Phi']]
+
         def step():
-            vb.prepare_project(data['X'], data['V'], data['Phi'], out=rho)
+            if model is None:
+                vb.prepare_project(data['X'], data['V'], data['Phi'], out=rho)
+            else:
+                vb.prepare_xvectors(data['X'], *model, out=rho)
             gamma[:, :w['S']].copy_(data['gamma0'])
             pi.copy_(pi0.expand_as(pi))
             out = vb.run(gamma, pi, Fa=w['Fa'], Fb=w['Fb'], loopProb=w['loopP'], maxIters=w['iters'], epsilon=-float('inf'))
@@ -394,7 +409,7 @@ def main():
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
     S = res['S']
     alg_bytes = {   # algorithmic bytes per frame per launch
-        'project': 4 * D_RAW + 4 * R_DIM,
+        'project': 4 * D_RAW + 4 * R_DIM if args.front == 'project' else 4 * D_RAW + 3 * 4 * R_DIM,
         'prepare': 4 * R_DIM,
         'mstep_partial': 4 * R_DIM + 4 * S,
         'loglik': 4 * R_DIM + 4 * S + 4,
@@ -426,7 +441,7 @@ def main():
 
     # ---- end-to-end through the host-buffer API (pinned host inputs, H2D + D2H inside the timed region) ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.front == 'project':
         hp = HostPipeline(res['lengths'], D_RAW, R_DIM, w['S'], device=device)
         Xh = torch.empty((N, D_RAW), dtype=torch.float32).pin_memory()
         Gh = torch.empty((N, w['S']), dtype=torch.float32).pin_memory()
@@ -495,7 +510,8 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic (seeded sticky-Markov speakers in PLDA space, SURVEY.md 8d; generated on the device)',
-            'config': workload_config(w, wname, world),
+            'config': workload_config(w, wname, world, note=None if args.front == 'project' else
+                                      'front end = vbx_prepare_xvectors (x-vector transform + PLDA projection) instead of rho = X.V; not the headline definition'),
             'target': {'north_star_x_vectors_per_s': 1e7, 'ratio': value / 1e7 / max(world, 1)},
             'roofline': roof, 'whole_step': whole, 'kernels': per_kernel, 'gpu_launches': res['launches'] * args.steps,
             'gpu_launches_per_step': res['launches'], 'clocks': res['clocks'], 'e2e': e2e, 'cpu_baseline': cpu,

@@ -81,6 +81,16 @@ int vbx_prepare_scale(vbx_handle_t h, const float *fea, const float *Phi, float 
 int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *V, const float *Phi,
                         float *rho_out, void *stream);
 
+/* The real-data caller chain in front of VBx() (VBx/vbhmm.py:125-129 x-vector transform, :153 PLDA projection)
+ * fused with the scale of VBx/VBx.py:88-89, as two tcgen05 passes (R must be 128, Dx a multiple of 32):
+ *   x_norm = l2norm(l2norm(x_raw - mean1) . lda - mean2)          x_raw [N,Dx], lda [Dx,128], x_norm [N,128]
+ *   rho    = ((x_norm - plda_mu) . plda_tr^T) * sqrt(plda_psi)    plda_tr [128,128] and plda_psi [128] are the
+ *            DIAGONALISED model (VBx/vbhmm.py:136-143; row n of plda_tr is output dimension n), Phi = plda_psi.
+ * x_norm_out and rho_out are distinct [N,128] device arrays; all pointers are device pointers. */
+int vbx_prepare_xvectors(vbx_handle_t h, const float *x_raw, int32_t Dx, const float *mean1, const float *lda,
+                         const float *mean2, const float *plda_mu, const float *plda_tr, const float *plda_psi,
+                         float *x_norm_out, float *rho_out, void *stream);
+
 /* The EM loop VBx/VBx.py:91-125 for every recording of the planned batch.
  *   rho       [N,R]   from vbx_prepare_*                                (VBx/VBx.py:89)
  *   Phi       [R]                                                        (VBx/VBx.py:30 `Phi`)

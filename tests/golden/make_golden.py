@@ -166,7 +166,25 @@ def synthetic_cases():
     np.savez_compressed(os.path.join(HERE, 'forward_backward_cases.npz'), **fb)
 
 
+def es2005a_model():
+    """The x-vector transform and the (diagonalised) PLDA of the shipped model, as the arrays VBx/vbhmm.py:125-143
+    works with: the inputs of the real-data chain test (x_raw of es2005a.npz -> fea of es2005a.npz)."""
+    plda_f = os.path.join(REF, 'VBx/models/ResNet101_16kHz/plda')
+    tr_f = os.path.join(REF, 'VBx/models/ResNet101_16kHz/transform.h5')
+    plda_mu, plda_tr, plda_psi = formats.read_kaldi_plda(plda_f)
+    W = np.linalg.inv(plda_tr.T.dot(plda_tr))
+    B = np.linalg.inv((plda_tr.T / plda_psi).dot(plda_tr))
+    acvar, wccn = eigh(B, W)
+    mean1, mean2, lda = formats.read_xvec_transform(tr_f)
+    np.savez_compressed(os.path.join(HERE, 'es2005a_model.npz'), mean1=mean1, mean2=mean2, lda=lda, plda_mu=plda_mu,
+                        plda_tr=wccn.T[::-1], plda_psi=acvar[::-1], sha_plda=sha(plda_f), sha_transform=sha(tr_f))
+
+
 if __name__ == '__main__':
     np.random.seed(0)
+    if sys.argv[1:] == ['model']:
+        es2005a_model()
+        sys.exit(0)
     es2005a()
+    es2005a_model()
     synthetic_cases()

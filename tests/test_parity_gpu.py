@@ -301,6 +301,60 @@ def test_projection_tcgen05(n_rec, T):
     vb.close()
 
 
+def _synthetic_xvector_model(rng, Dx=256):
+    """A model with the shapes of the shipped one (VBx/models/ResNet101_16kHz: 256 -> LDA 128 -> PLDA 128)."""
+    mean1 = rng.standard_normal(Dx) * 0.5
+    lda = rng.standard_normal((Dx, 128)) / np.sqrt(Dx)
+    mean2 = rng.standard_normal(128) * 0.05
+    plda_mu = rng.standard_normal(128) * 0.02
+    q, _ = np.linalg.qr(rng.standard_normal((128, 128)))
+    plda_tr = q * rng.uniform(2.0, 20.0, 128)[:, None]        # already-diagonalised model: any full-rank transform
+    plda_psi = synth.plda_phi(128).astype(np.float64)
+    return mean1, lda, mean2, plda_mu, plda_tr, plda_psi
+
+
+@pytest.mark.parametrize('n_rec,T', [(3, 77), (1, 256), (200, 1000)])
+def test_xvector_chain_tcgen05(n_rec, T):
+    """vbx_prepare_xvectors (VBx/vbhmm.py:125-129,153 + VBx/VBx.py:88-89 on the tensor cores) against the float64
+    host chain of vbx_b200.pipeline, then the EM loop on top of it against the oracle."""
+    from vbx_b200.batch import VbxBatch
+    from vbx_b200 import pipeline
+    rng = np.random.default_rng(101 + T)
+    lens = [T] * n_rec
+    N = n_rec * T
+    mean1, lda, mean2, mu, tr, psi = _synthetic_xvector_model(rng)
+    x_raw = (rng.standard_normal((N, 256)) * 2.0 + mean1[None, :]).astype(np.float32)
+    f32 = lambda a: cuda(np.ascontiguousarray(a, dtype=np.float32))
+    t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).double()   # the float32 model, in float64
+    xn64 = pipeline.xvector_transform(t64(x_raw), t64(mean1), t64(mean2), t64(lda))
+    fea64 = pipeline.plda_project(xn64, t64(mu), t64(tr), 128).numpy()
+    xn64 = xn64.numpy()
+    psi32 = t64(psi).numpy()
+    rho64 = fea64 * np.sqrt(psi32)[None, :]
+    S = 4
+    vb = VbxBatch(lens, 128, S, device=dev())
+    rho, x_norm = vb.prepare_xvectors(cuda(x_raw), f32(mean1), f32(lda), f32(mean2), f32(mu), f32(tr), f32(psi))
+    torch.cuda.synchronize()
+    e1 = np.abs(x_norm.double().cpu().numpy() - xn64).max() / np.abs(xn64).max()
+    e2 = np.abs(rho.double().cpu().numpy() - rho64).max() / np.abs(rho64).max()
+    print("x-vector chain error: x_norm %.2e, rho %.2e" % (e1, e2))
+    assert e1 <= 5e-6, e1
+    assert e2 <= 1e-5, e2
+    assert np.abs(np.linalg.norm(x_norm.double().cpu().numpy(), axis=1) - 1.0).max() <= 1e-6
+    if N <= 4096:      # EM on top (G comes from the fused epilogue): compare with the oracle on the float64 features
+        offsets = np.concatenate([[0], np.cumsum(lens)])
+        g0 = rng.random((N, S))
+        g0 /= g0.sum(1, keepdims=True)
+        ref = co.vbx_oracle_batch(fea64, psi32, offsets, g0, np.full(S, 1.0 / S), 0.3, 17.0, 0.99, 5, -np.inf)
+        g = cuda(g0.astype(np.float32))
+        p = torch.full((n_rec, S), 1.0 / S, device=dev())
+        out = vb.run(g, p, Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=5, epsilon=-np.inf)
+        torch.cuda.synchronize()
+        assert np.abs(g.double().cpu().numpy() - ref['gamma']).max() <= G_TOL
+        check_elbo(out['Li'].cpu().numpy(), ref['Li'])
+    vb.close()
+
+
 def test_full_pipeline_from_raw_xvectors():
     """X (D=256) -> rho = X.V -> EM: equals the oracle run on fea = X.V0."""
     from vbx_b200.batch import VbxBatch

@@ -87,3 +87,41 @@ def test_es2005a_rttm_end_to_end_on_gpu(es):
         assert mapping.setdefault(int(mine), int(ref)) == int(ref)
     assert len(set(mapping.values())) == len(mapping) == 5
     vb.close()
+
+
+@pytest.mark.gpu
+def test_es2005a_raw_xvectors_to_rttm_on_gpu(es):
+    """The whole real-data path on the device: raw x-vectors of exp/ES2005a.ark -> fused tcgen05 x-vector transform +
+    PLDA projection (vbx_prepare_xvectors, VBx/vbhmm.py:125-129,153) -> VB-HMM -> RTTM, against the features and
+    the system output the reference produces (tests/golden/make_golden.py)."""
+    from vbx_b200.batch import VbxBatch
+    m = np.load(os.path.join(GOLD, 'es2005a_model.npz'))
+    assert str(m['sha_plda']) == str(es['sha_plda']) and str(m['sha_transform']) == str(es['sha_transform'])
+    dev = torch.device('cuda:0')
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    T = es['x_raw'].shape[0]
+    vb = VbxBatch([T], 128, 4, device=dev)
+    rho, x_norm = vb.prepare_xvectors(f32(es['x_raw']), f32(m['mean1']), f32(m['lda']), f32(m['mean2']),
+                                      f32(m['plda_mu']), f32(m['plda_tr']), f32(m['plda_psi']))
+    torch.cuda.synchronize()
+    # The shipped LDA matrix is badly conditioned (sum |a_k lda_kn| ~ 1000 x |sum|), so float32-level arithmetic shows:
+    # numpy float32 reaches 3.9e-6 / 3.6e-5 on these two checks; split-precision TF32 carries 22 operand bits, 4x that.
+    e_x = np.abs(x_norm.double().cpu().numpy() - es['x_lda']).max()
+    fea = rho.double().cpu().numpy() / np.sqrt(es['Phi'])[None, :]
+    e_f = np.abs(fea - es['fea']).max()
+    print('ES2005a chain: max |x_norm - ref| = %.2e, max |fea - ref| = %.2e (max |fea| = %.2f)' % (e_x, e_f, np.abs(es['fea']).max()))
+    assert e_x <= 1.5e-5
+    assert e_f <= 3e-4
+    vb.close()
+    lines, labels, g = pipeline.diarize_recording(
+        es['x_raw'], es['seg_times'], es['labels_ahc'], (m['mean1'], m['mean2'], m['lda']),
+        (m['plda_mu'], m['plda_tr'], m['plda_psi']), float(es['Fa']), float(es['Fb']), float(es['loopProb']),
+        smoothing=float(es['smoothing']), max_iters=40, epsilon=1e-6, device=dev, recording='ES2005a',
+        chain='tcgen05', plda_is_diagonal=True)
+    assert np.array_equal(labels, es['labels'])
+    e_g = np.abs(g.double().cpu().numpy() - es['gamma']).max()
+    print('ES2005a chain: max |gamma - ref| = %.2e' % e_g)
+    assert e_g <= 5e-3
+    assert len(lines) == 50 and all(l.startswith('SPEAKER ES2005a 1 ') for l in lines)
+    starts = np.array([float(l.split()[3]) for l in lines])
+    np.testing.assert_allclose(starts, es['rttm_starts'], atol=1e-3)

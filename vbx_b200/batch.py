@@ -129,6 +129,27 @@ class VbxBatch:
         self.rho, self.Phi = rho, Phi
         return rho
 
+    def prepare_xvectors(self, x_raw, mean1, lda, mean2, plda_mu, plda_tr, plda_psi, out=None):
+        """The real-data chain in front of VBx() on the tensor cores (VBx/vbhmm.py:125-129 and :153, with the scale
+        of VBx/VBx.py:88-89): raw x-vectors [N,Dx] -> rho [N,128].  plda_tr / plda_psi are the diagonalised model
+        (pipeline.diagonalise_plda).  Returns (rho, x_norm); x_norm is the l2-normalised LDA output [N,128]."""
+        Dx = int(x_raw.shape[1])
+        self._f32(x_raw, (self.N, Dx), 'x_raw')
+        self._f32(mean1, (Dx,), 'mean1')
+        self._f32(lda, (Dx, 128), 'lda')
+        self._f32(mean2, (128,), 'mean2')
+        self._f32(plda_mu, (128,), 'plda_mu')
+        self._f32(plda_tr, (128, 128), 'plda_tr')
+        self._f32(plda_psi, (128,), 'plda_psi')
+        rho = torch.empty((self.N, self.R), dtype=torch.float32, device=self.device) if out is None \
+            else self._f32(out, (self.N, self.R), 'out')
+        x_norm = torch.empty((self.N, 128), dtype=torch.float32, device=self.device)
+        self._check(self.lib.vbx_prepare_xvectors(self._h, _ptr(x_raw), Dx, _ptr(mean1), _ptr(lda), _ptr(mean2),
+                                                  _ptr(plda_mu), _ptr(plda_tr), _ptr(plda_psi), _ptr(x_norm), _ptr(rho),
+                                                  self._stream()))
+        self.rho, self.Phi = rho, plda_psi
+        return rho, x_norm
+
     # ---- VBx/VBx.py:91-125 ----------------------------------------------------------------
     def run(self, gamma, pi, Fa=1.0, Fb=1.0, loopProb=0.9, maxIters=10, epsilon=1e-4,
             alpha=None, invL=None, warm_start=False, return_model=False):

@@ -374,6 +374,35 @@ int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *
     return VBX_OK;
 }
 
+int vbx_prepare_xvectors(vbx_handle_t h, const float *x_raw, int32_t Dx, const float *mean1, const float *lda,
+                         const float *mean2, const float *plda_mu, const float *plda_tr, const float *plda_psi,
+                         float *x_norm_out, float *rho_out, void *stream) {
+    int rc = check_ready(h, "vbx_prepare_xvectors");
+    if (rc) return rc;
+    if (!mean1 || !lda || !mean2 || !plda_mu || !plda_tr || !plda_psi)
+        return fail(h, VBX_ERR_ARG, "vbx_prepare_xvectors: null model pointer");
+    if (h->plan.n_frames && (!x_raw || !x_norm_out || !rho_out)) return fail(h, VBX_ERR_ARG, "vbx_prepare_xvectors: null pointer");
+    if (x_norm_out && x_norm_out == rho_out) return fail(h, VBX_ERR_ARG, "vbx_prepare_xvectors: x_norm_out and rho_out must not alias");
+    if (Dx < 32 || (Dx & 31)) return fail(h, VBX_ERR_ARG, "vbx_prepare_xvectors: Dx must be a multiple of 32");
+    if (h->plan.R != 128) return fail(h, VBX_ERR_ARG, "vbx_prepare_xvectors: the plan must have R == 128");
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        Timed t(h, st, VBX_K_PROJECT);
+        std::string why;
+        int n = vbx::launch_xvector_chain_tcgen05(h->plan, x_raw, Dx, mean1, lda, mean2, plda_mu, plda_tr, plda_psi,
+                                                  x_norm_out, rho_out, h->ws.rowmax, st, &why);
+        if (n < 0) return fail(h, VBX_ERR_CUDA, "vbx_prepare_xvectors: " + why);
+        h->launches += n;
+    }
+    {
+        Timed t(h, st, VBX_K_PREPARE);
+        rc = counted(h, vbx::launch_gsum_from_frames(h->plan, h->ws, h->ws.rowmax, st), "gsum_from_frames");
+    }
+    if (rc) return rc;
+    h->prepared = true;
+    return VBX_OK;
+}
+
 int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io, float *pi_io,
             const int32_t *n_states, double Fa, double Fb, double loop_prob, int32_t max_iters, double epsilon,
             float *alpha_io, float *invL_io, int32_t warm_start, double *Li_out, int32_t *n_iters_out,

@@ -172,6 +172,9 @@ int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const dou
 // tcgen05 projection (vbx_project_tc.cu)
 int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, const float *Phi, float *rho,
                            float *gframe, cudaStream_t st, std::string *err);
+int launch_xvector_chain_tcgen05(const Plan &pl, const float *x_raw, int Dx, const float *mean1, const float *lda,
+                                 const float *mean2, const float *plda_mu, const float *plda_tr, const float *psi,
+                                 float *x_norm, float *rho, float *gframe, cudaStream_t st, std::string *err);
 int launch_gsum_from_frames(const Plan &pl, const Workspace &ws, const float *gframe, cudaStream_t st);
 
 }  // namespace vbx

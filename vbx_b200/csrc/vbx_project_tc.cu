@@ -3,7 +3,10 @@
 // breaks the 1e-4 parity bar of the EM loop (hard part 4).
 // Reference: the caller-side projection VBx/vbhmm.py:129,153 folded with the scale VBx/VBx.py:88-89.
 //
-// One persistent CTA per SM, 13 warps:
+// The same kernel, templated on MODE, also runs the real-data front end (x-vector transform and PLDA projection,
+// VBx/vbhmm.py:125-129,153; launch_xvector_chain_tcgen05 below).
+//
+// One persistent CTA per SM, 17 warps:
 //   warps 0-7  producers: coalesced LDG of a 256-frame x 32-column block of X (prefetched one block ahead in
 //              registers), split into TF32 hi/lo, stored into the 128B-swizzled K-major UMMA layout;
 //              thread 0 also issues the bulk-async (TMA, cp.async.bulk) copies of the pre-split V block.
@@ -98,6 +101,25 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// 32 consecutive fp32 TMEM columns of this warp's 32 lanes (lane = accumulator row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void split_rn(const float x, float &hi, float &lo) {
     const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     hi = __uint_as_float(h);
@@ -119,15 +141,24 @@ __global__ void build_v_images_kernel(const float *__restrict__ V, int D, float 
     }
 }
 
+// MODE 0  rho = X . V, G_t from rho and Phi                                   (the projection of SURVEY 8d)
+// MODE 2  rho = (X - a_off) . V, G_t as above                                  (PLDA stage, VBx/vbhmm.py:153)
+// MODE 1  out = l2norm(l2norm(X - a_off) . V - e_off)                          (x-vector transform, VBx/vbhmm.py:125-129)
+//         the producers also accumulate ||x - a_off||^2 per row and hand it to the epilogue through shared memory
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vimg, float *__restrict__ rho, int64_t N,
-                       int D, const float *__restrict__ Phi, float *__restrict__ gframe) {
+                       int D, const float *__restrict__ Phi, float *__restrict__ gframe,
+                       const float *__restrict__ a_off, const float *__restrict__ e_off) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte aligned stage buffers (required by the 128-byte swizzle)
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // the stage buffers must be 1024-byte aligned (128-byte swizzle); the dynamic window starts at offset 0 of the
+    // CTA's shared memory (no static __shared__ in this kernel), which is checked rather than padded for
+    uint8_t *smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
-    float *s_inv_phi = reinterpret_cast<float *>(bars + 18);   // 128 floats
+    float *s_inv_phi = reinterpret_cast<float *>(bars + 18);   // 128 floats: 1/Phi (MODE 0, 2) or e_off (MODE 1)
+    float *s_n1 = reinterpret_cast<float *>(smem + kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes);   // [2][256]
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     // barrier ids
@@ -141,7 +172,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
     const int n_kb = D / kKB;
     const int64_t n_tiles = (N + kTileM - 1) / kTileM;
 
-    if (tid < 128) s_inv_phi[tid] = 1.f / Phi[tid];
+    if (tid < 128) s_inv_phi[tid] = MODE == 1 ? e_off[tid] : 1.f / Phi[tid];
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_a(s), kProducerThreads);
@@ -173,6 +204,9 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
         const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t n_blocks = my_tiles * n_kb;
         float4 bufA[8], bufB[8];
+        float ss[8];                      // MODE 1: running ||x - a_off||^2 of this thread's 8 rows (its 4 columns)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss[i] = 0.f;
         auto issue = [&](const int64_t b, float4(&buf)[8]) {
             if (b >= n_blocks) return;
             const int64_t tile = blockIdx.x + (b / n_kb) * gridDim.x;
@@ -188,6 +222,8 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
             const int s = (int)(b & 1);
             const uint32_t ph = (uint32_t)((b >> 1) & 1);
             const int kb = (int)(b % n_kb);
+            float4 aoff = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE != 0) aoff = __ldg(reinterpret_cast<const float4 *>(a_off + kb * kKB) + c);
             mbar_wait(empty(s), ph ^ 1);               // the MMAs that read this stage have completed
             const uint32_t stage = smem_base + s * kStageBytes;
             if (tid == 0) {
@@ -198,14 +234,34 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
             for (int i = 0; i < 8; ++i) {
                 const int r = r0 + 32 * i;             // 0..255
                 const int mt = r >> 7, m = r & 127;
-                float4 hi, lo;
-                split_rn(buf[i].x, hi.x, lo.x);
-                split_rn(buf[i].y, hi.y, lo.y);
-                split_rn(buf[i].z, hi.z, lo.z);
-                split_rn(buf[i].w, hi.w, lo.w);
+                float4 hi, lo, x = buf[i];
+                if (MODE != 0) {
+                    x.x -= aoff.x;
+                    x.y -= aoff.y;
+                    x.z -= aoff.z;
+                    x.w -= aoff.w;
+                }
+                if (MODE == 1) ss[i] = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ss[i]))));
+                split_rn(x.x, hi.x, lo.x);
+                split_rn(x.y, hi.y, lo.y);
+                split_rn(x.z, hi.z, lo.z);
+                split_rn(x.w, hi.w, lo.w);
                 const uint32_t off = (uint32_t)(m * 128 + ((c ^ (m & 7)) << 4));
                 st_shared_v4(stage + (mt * 2 + 0) * kABytes + off, hi);
                 st_shared_v4(stage + (mt * 2 + 1) * kABytes + off, lo);
+            }
+            if (MODE == 1 && kb == n_kb - 1) {
+                // row norms of the finished tile: the 8 lanes that share a row are adjacent
+                float *dst = s_n1 + ((b / n_kb) & 1) * kTileM;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float v = ss[i];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    if (c == 0) dst[r0 + 32 * i] = v;
+                    ss[i] = 0.f;
+                }
             }
             fence_proxy_async_smem();                  // make the generic-proxy stores visible to the tensor core
             mbar_arrive(full_a(s));
@@ -275,38 +331,10 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
             mbar_wait(tmem_full(acc), acc_ph);
             tc_fence_after();
             const int64_t row_base = tile * kTileM + mt * 128 + quarter * 32;
-            float n2 = 0.f;                              // ||fea||^2 = sum_r rho^2 / Phi_r   (VBx/VBx.py:87)
-#pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + mt * 128 + cb * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // lane = row: G_t partial sum and the swizzled stage (chunk j of row r at position j ^ (r & 7))
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 ip;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ip.x), "=f"(ip.y), "=f"(ip.z), "=f"(ip.w)
-                                 : "r"(inv_phi_s + (uint32_t)(cb * 32 + 4 * j) * 4));
-                    const float4 x = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                    n2 = fmaf(x.x * x.x, ip.x, n2);
-                    n2 = fmaf(x.y * x.y, ip.y, n2);
-                    n2 = fmaf(x.z * x.z, ip.z, n2);
-                    n2 = fmaf(x.w * x.w, ip.w, n2);
-                    st_shared_v4(epi + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), x);
-                }
+            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + mt * 128);
+            // lane = row.  8 lanes then cover the 128 bytes of one row: every store instruction writes 4 full lines
+            auto store_block = [&](const int cb) {
                 __syncwarp();
-                // 8 lanes cover the 128 bytes of one row: every store instruction writes 4 full lines
                 const int cc = lane & 7, rr = lane >> 3;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -317,8 +345,64 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
                     if (row_base + r < N) *reinterpret_cast<float4 *>(rho + (row_base + r) * 128 + cb * 32 + 4 * cc) = x;
                 }
                 __syncwarp();
+            };
+            if (MODE == 1) {
+                // y = acc / ||x - mean1|| - mean2 ; out = y / ||y||   (two passes over the TMEM accumulator)
+                const float inv_n1 = 1.f / sqrtf(s_n1[acc * kTileM + mt * 128 + quarter * 32 + lane]);
+                float n2 = 0.f;
+#pragma unroll 1
+                for (int cb = 0; cb < 4; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(tbase + (uint32_t)(cb * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 e = ld_shared_v4(inv_phi_s + (uint32_t)(cb * 32 + 4 * j) * 4);
+                        const float y0 = fmaf(__uint_as_float(v[4 * j]), inv_n1, -e.x);
+                        const float y1 = fmaf(__uint_as_float(v[4 * j + 1]), inv_n1, -e.y);
+                        const float y2 = fmaf(__uint_as_float(v[4 * j + 2]), inv_n1, -e.z);
+                        const float y3 = fmaf(__uint_as_float(v[4 * j + 3]), inv_n1, -e.w);
+                        n2 = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, n2))));
+                    }
+                }
+                const float inv_n2 = 1.f / sqrtf(n2);
+#pragma unroll 1
+                for (int cb = 0; cb < 4; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(tbase + (uint32_t)(cb * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 e = ld_shared_v4(inv_phi_s + (uint32_t)(cb * 32 + 4 * j) * 4);
+                        float4 x;
+                        x.x = fmaf(__uint_as_float(v[4 * j]), inv_n1, -e.x) * inv_n2;
+                        x.y = fmaf(__uint_as_float(v[4 * j + 1]), inv_n1, -e.y) * inv_n2;
+                        x.z = fmaf(__uint_as_float(v[4 * j + 2]), inv_n1, -e.z) * inv_n2;
+                        x.w = fmaf(__uint_as_float(v[4 * j + 3]), inv_n1, -e.w) * inv_n2;
+                        st_shared_v4(epi + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), x);
+                    }
+                    store_block(cb);
+                }
+            } else {
+                float n2 = 0.f;                          // ||fea||^2 = sum_r rho^2 / Phi_r   (VBx/VBx.py:87)
+#pragma unroll 1
+                for (int cb = 0; cb < 4; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(tbase + (uint32_t)(cb * 32), v);
+                    // G_t partial sum and the swizzled stage (chunk j of row r at position j ^ (r & 7))
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 ip = ld_shared_v4(inv_phi_s + (uint32_t)(cb * 32 + 4 * j) * 4);
+                        const float4 x = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        n2 = fmaf(x.x * x.x, ip.x, n2);
+                        n2 = fmaf(x.y * x.y, ip.y, n2);
+                        n2 = fmaf(x.z * x.z, ip.z, n2);
+                        n2 = fmaf(x.w * x.w, ip.w, n2);
+                        st_shared_v4(epi + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), x);
+                    }
+                    store_block(cb);
+                }
+                if (row_base + lane < N) gframe[row_base + lane] = -0.5f * (n2 + 128.f * 1.8378770664093453f);   // G_t, R = 128
             }
-            if (row_base + lane < N) gframe[row_base + lane] = -0.5f * (n2 + 128.f * 1.8378770664093453f);   // G_t, R = 128
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));
             if (++acc == 2) {
@@ -335,13 +419,73 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
     }
 }
 
+// V2[k,n] = tr[n,k] * sqrt(psi[n]): the PLDA projection (x - mu) . tr^T (VBx/vbhmm.py:153) folded with the
+// scale rho = fea * sqrt(Phi) (VBx/VBx.py:89)
+__global__ void build_plda_v_kernel(const float *__restrict__ tr, const float *__restrict__ psi, float *__restrict__ V2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 128 * 128) {
+        const int k = i >> 7, n = i & 127;
+        V2[i] = tr[n * 128 + k] * sqrtf(psi[n]);
+    }
+}
+
 struct TcState {
     float *vimg = nullptr;
     size_t vimg_bytes = 0;
+    float *v2 = nullptr;
     int device = -1;
-    bool configured = false;
+    bool configured[3] = {false, false, false};
 };
 TcState g_tc[16];
+
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes + 2 * kTileM * 4;
+
+TcState *tc_state(size_t need_img, std::string *err) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) {
+        if (err) *err = "device index out of range";
+        return nullptr;
+    }
+    TcState &tc = g_tc[dev];
+    if (tc.vimg_bytes < need_img) {
+        if (tc.vimg) cudaFree(tc.vimg);
+        tc.vimg = nullptr;
+        if (cudaMalloc(&tc.vimg, need_img) != cudaSuccess) {
+            if (err) *err = "cudaMalloc(V images) failed";
+            tc.vimg_bytes = 0;
+            return nullptr;
+        }
+        tc.vimg_bytes = need_img;
+    }
+    tc.device = dev;
+    return &tc;
+}
+
+// one GEMM pass [N,D] x [D,128] of the given MODE; V is row-major [D,128] in device memory
+template <int MODE>
+int launch_gemm_tc(TcState &tc, int64_t N, const float *X, int D, const float *V, const float *Phi, float *out, float *gframe,
+                   const float *a_off, const float *e_off, cudaStream_t st, std::string *err) {
+    if (!tc.configured[MODE]) {
+        if (cudaFuncSetAttribute(project_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) !=
+            cudaSuccess) {
+            if (err) *err = "cudaFuncSetAttribute(smem) failed";
+            return -1;
+        }
+        tc.configured[MODE] = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, tc.device);
+    build_v_images_kernel<<<D / kKB, 256, 0, st>>>(V, D, tc.vimg);
+    const int64_t n_tiles = (N + kTileM - 1) / kTileM;
+    const int grid = (int)std::min<int64_t>(n_tiles, sms);
+    project_tcgen05_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(X, tc.vimg, out, N, D, Phi, gframe, a_off, e_off);
+    if (cudaGetLastError() != cudaSuccess) {
+        if (err) *err = "tcgen05 projection launch failed";
+        return -1;
+    }
+    return 2;
+}
 
 }  // namespace
 
@@ -356,43 +500,39 @@ int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V
         return -1;
     }
     if (pl.n_frames == 0) return 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16) {
-        if (err) *err = "device index out of range";
+    TcState *tc = tc_state((size_t)(D / kKB) * 2 * kABytes, err);
+    if (!tc) return -1;
+    return launch_gemm_tc<0>(*tc, pl.n_frames, X, D, V, Phi, rho, gframe, nullptr, nullptr, st, err);
+}
+
+// The caller-side chain of VBx/vbhmm.py:125-129,153 plus the scale of VBx/VBx.py:88-89 as two tensor-core passes:
+//   x_norm = l2norm(l2norm(x_raw - mean1) . lda - mean2)             [N,128]
+//   rho    = (x_norm - plda_mu) . (plda_tr^T * sqrt(psi))            [N,128], with G_t per frame
+int launch_xvector_chain_tcgen05(const Plan &pl, const float *x_raw, int Dx, const float *mean1, const float *lda,
+                                 const float *mean2, const float *plda_mu, const float *plda_tr, const float *psi,
+                                 float *x_norm, float *rho, float *gframe, cudaStream_t st, std::string *err) {
+    if (pl.R != 128) {
+        if (err) *err = "the x-vector chain needs R == 128";
         return -1;
     }
-    TcState &tc = g_tc[dev];
-    const size_t need = (size_t)(D / kKB) * 2 * kABytes;
-    if (tc.vimg_bytes < need) {
-        if (tc.vimg) cudaFree(tc.vimg);
-        tc.vimg = nullptr;
-        if (cudaMalloc(&tc.vimg, need) != cudaSuccess) {
-            if (err) *err = "cudaMalloc(V images) failed";
-            tc.vimg_bytes = 0;
-            return -1;
-        }
-        tc.vimg_bytes = need;
-    }
-    const int smem = kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes + 1024;
-    if (!tc.configured) {
-        if (cudaFuncSetAttribute(project_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-            if (err) *err = "cudaFuncSetAttribute(smem) failed";
-            return -1;
-        }
-        tc.configured = true;
-    }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    build_v_images_kernel<<<D / kKB, 256, 0, st>>>(V, D, tc.vimg);
-    const int64_t n_tiles = (pl.n_frames + kTileM - 1) / kTileM;
-    const int grid = (int)std::min<int64_t>(n_tiles, sms);
-    project_tcgen05_kernel<<<grid, kThreads, smem, st>>>(X, tc.vimg, rho, pl.n_frames, D, Phi, gframe);
-    if (cudaGetLastError() != cudaSuccess) {
-        if (err) *err = "tcgen05 projection launch failed";
+    if (Dx % kKB != 0 || Dx < kKB) {
+        if (err) *err = "the x-vector chain needs the x-vector dimension to be a multiple of 32";
         return -1;
     }
-    return 2;
+    if (pl.n_frames == 0) return 0;
+    TcState *tc = tc_state((size_t)(std::max(Dx, 128) / kKB) * 2 * kABytes, err);
+    if (!tc) return -1;
+    if (!tc->v2 && cudaMalloc(&tc->v2, 128 * 128 * sizeof(float)) != cudaSuccess) {
+        if (err) *err = "cudaMalloc(V2) failed";
+        tc->v2 = nullptr;
+        return -1;
+    }
+    int n = launch_gemm_tc<1>(*tc, pl.n_frames, x_raw, Dx, lda, nullptr, x_norm, nullptr, mean1, mean2, st, err);
+    if (n < 0) return -1;
+    build_plda_v_kernel<<<64, 256, 0, st>>>(plda_tr, psi, tc->v2);
+    int m = launch_gemm_tc<2>(*tc, pl.n_frames, x_norm, 128, tc->v2, psi, rho, gframe, plda_mu, nullptr, st, err);
+    if (m < 0) return -1;
+    return n + m + 1;
 }
 
 }  // namespace vbx
