@@ -108,6 +108,12 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
             float *alpha_io, float *invL_io, int32_t warm_start, double *Li_out, int32_t *n_iters_out,
             int32_t *flags_out, void *stream);
 
+/* Output step, VBx/vbhmm.py:160-162: first_out[t] = argsort(-gamma[t])[0], second_out[t] = argsort(-gamma[t])[1]
+ * over the live states of the frame's recording (second_out may be NULL; -1 when the recording has one state).
+ * gamma [N,S] as left by vbx_run, n_states [n_rec] or NULL, outputs int32 [N]; all device pointers. */
+int vbx_hard_labels(vbx_handle_t h, const float *gamma, const int32_t *n_states, int32_t *first_out,
+                    int32_t *second_out, void *stream);
+
 /* Float64 evaluation of the same EM loop ("exact" mode for the one-recording-per-call use of VBx/vbhmm.py:154-158,
  * where the reference stops on an ELBO improvement < 1e-6, VBx/vbhmm.py:157 -- below float32 resolution).
  * All arrays float64: fea [N,R] (the reference's X, VBx/VBx.py:30), Phi [R], gamma_io [N,S], pi_io [n_rec,S],

@@ -355,6 +355,31 @@ def test_xvector_chain_tcgen05(n_rec, T):
     vb.close()
 
 
+def test_hard_labels_kernel():
+    """vbx_hard_labels == argsort(-q)[:, 0] / [:, 1] (VBx/vbhmm.py:160-162) on a ragged batch with per-recording
+    state counts; padded columns never win even when they hold garbage."""
+    from vbx_b200.batch import VbxBatch
+    rng = np.random.default_rng(5)
+    lens = [1, 63, 64, 65, 300, 2]
+    ns = [3, 5, 1, 7, 6, 2]
+    vb = VbxBatch(lens, 128, ns, device=dev())
+    N, S = sum(lens), vb.S
+    g = rng.random((N, S)).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    first, second = vb.hard_labels(cuda(g), second=True)
+    torch.cuda.synchronize()
+    first, second = first.cpu().numpy(), second.cpu().numpy()
+    for b, n in enumerate(ns):
+        q = g[off[b]:off[b + 1], :n]
+        order = np.argsort(-q, axis=1, kind='stable')
+        assert np.array_equal(first[off[b]:off[b + 1]], order[:, 0])
+        if n > 1:
+            assert np.array_equal(second[off[b]:off[b + 1]], order[:, 1])
+        else:
+            assert np.all(second[off[b]:off[b + 1]] == -1)
+    vb.close()
+
+
 def test_full_pipeline_from_raw_xvectors():
     """X (D=256) -> rho = X.V -> EM: equals the oracle run on fea = X.V0."""
     from vbx_b200.batch import VbxBatch

@@ -83,6 +83,15 @@ class VbxBatch:
     def set_option(self, name, value):
         self._check(self.lib.vbx_set_option(self._h, name.encode(), int(value)))
 
+    def hard_labels(self, gamma, second=False):
+        """VBx/vbhmm.py:160-162 on the device: the most likely speaker per frame (int32 [N]); with second=True also
+        the runner-up.  Only these labels need to leave the GPU, not gamma."""
+        self._f32(gamma, (self.N, self.S), 'gamma')
+        first = torch.empty(self.N, dtype=torch.int32, device=self.device)
+        sec = torch.empty(self.N, dtype=torch.int32, device=self.device) if second else None
+        self._check(self.lib.vbx_hard_labels(self._h, _ptr(gamma), _ptr(self.n_states), _ptr(first), _ptr(sec), self._stream()))
+        return (first, sec) if second else first
+
     @property
     def launches(self):
         return int(self.lib.vbx_launch_count(self._h))

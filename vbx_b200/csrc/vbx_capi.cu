@@ -460,6 +460,14 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
     return VBX_OK;
 }
 
+int vbx_hard_labels(vbx_handle_t h, const float *gamma, const int32_t *n_states, int32_t *first_out,
+                    int32_t *second_out, void *stream) {
+    if (!h) return VBX_ERR_ARG;
+    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_hard_labels: call vbx_plan first");
+    if (h->plan.n_frames && (!gamma || !first_out)) return fail(h, VBX_ERR_ARG, "vbx_hard_labels: null pointer");
+    return counted(h, vbx::launch_hard_labels(h->plan, gamma, n_states, first_out, second_out, (cudaStream_t)stream), "hard_labels");
+}
+
 int vbx_f64_workspace_bytes(vbx_handle_t h, size_t *bytes_out) {
     if (!h || !bytes_out) return VBX_ERR_ARG;
     if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_f64_workspace_bytes: call vbx_plan first");

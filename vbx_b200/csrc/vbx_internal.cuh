@@ -169,6 +169,8 @@ int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const dou
                    const int32_t *n_states, double Fa, double Fb, double loopP, int max_iters, double epsilon,
                    double *alpha_io, double *invL_io, int warm, double *Li, int32_t *n_iters, int32_t *flags,
                    cudaStream_t st);
+int launch_hard_labels(const Plan &pl, const float *gamma, const int32_t *n_states, int32_t *first, int32_t *second,
+                       cudaStream_t st);
 // tcgen05 projection (vbx_project_tc.cu)
 int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, const float *Phi, float *rho,
                            float *gframe, cudaStream_t st, std::string *err);

@@ -250,6 +250,49 @@ int launch_run_init(const Plan &pl, const Workspace &ws, const float *gamma, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// Output step: the most and second most likely speaker per frame,
+// labels1st = argsort(-q)[:, 0], labels2nd = argsort(-q)[:, 1]                       VBx/vbhmm.py:160-162
+// One thread per frame of a 64-frame tile; only the recording's live states compete (ties: lowest index).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLTile) hard_labels_kernel(Plan pl, const float *__restrict__ gamma,
+                                                             const int32_t *__restrict__ n_states,
+                                                             int32_t *__restrict__ first, int32_t *__restrict__ second) {
+    const int tile = blockIdx.x;
+    const int rec = pl.ltile_rec[tile];
+    const int64_t f0 = pl.ltile_f0[tile];
+    const int len = (int)min((int64_t)kLTile, pl.offsets[rec + 1] - f0);
+    if ((int)threadIdx.x >= len) return;
+    const int S = pl.S, ns = n_states ? n_states[rec] : S;
+    const float4 *row = reinterpret_cast<const float4 *>(gamma + (f0 + threadIdx.x) * S);
+    float b1 = -INFINITY, b2 = -INFINITY;
+    int i1 = -1, i2 = -1;
+    for (int q = 0; q < S / 4; ++q) {
+        const float4 v = row[q];
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int s = 4 * q + e;
+            if (s >= ns) break;
+            if (x[e] > b1) {
+                b2 = b1, i2 = i1;
+                b1 = x[e], i1 = s;
+            } else if (x[e] > b2) {
+                b2 = x[e], i2 = s;
+            }
+        }
+    }
+    first[f0 + threadIdx.x] = i1;
+    if (second) second[f0 + threadIdx.x] = i2;
+}
+
+int launch_hard_labels(const Plan &pl, const float *gamma, const int32_t *n_states, int32_t *first, int32_t *second,
+                       cudaStream_t st) {
+    if (pl.n_ltiles == 0) return 0;
+    hard_labels_kernel<<<pl.n_ltiles, kLTile, 0, st>>>(pl, gamma, n_states, first, second);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // M-step accumulation: partial[tile][s][r] = sum_{t in tile} gamma[t,s] * rho[t,r]      VBx/VBx.py:96
 // One CTA per <=256-frame tile of one recording.  A warp owns a frame slot and SPT states; lane owns
 // 4 consecutive r (the rho row is one coalesced 512 B request), gamma values are warp-uniform loads.

@@ -115,7 +115,7 @@ def diarize_recording(x_raw, seg_times, ahc_labels, transform, plda, Fa, Fb, loo
     else:
         raise ValueError("chain must be 'tcgen05' or 'float64'")
     vb.run(g, p, Fa=Fa, Fb=Fb, loopProb=loopP, maxIters=max_iters, epsilon=epsilon)
-    labels = hard_labels(g[:, :S]).cpu().numpy()
+    labels = vb.hard_labels(g).cpu().numpy().astype(np.int64)      # only the labels leave the device
     s, e, l = merge_adjacent_labels(seg_times[:, 0], seg_times[:, 1], labels)
     vb.close()
     return rttm_lines(recording, s, e, l), labels, g[:, :S]
