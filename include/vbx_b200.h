@@ -108,6 +108,19 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
             float *alpha_io, float *invL_io, int32_t warm_start, double *Li_out, int32_t *n_iters_out,
             int32_t *flags_out, void *stream);
 
+/* AHC initialisation, VBx/vbhmm.py:131-146, for every recording of the planned batch, in float64 like the reference:
+ *   cosine similarity of the recording's rows of x (VBx/diarization_lib.py:190-213; x [N,dim], float32 or float64),
+ *   thr_out[b] = twoGMMcalib_lin(similarities)[0] (VBx/diarization_lib.py:13-31, 20 iterations),
+ *   Z_out = fastcluster.linkage(squareform(-similarity), method='average') in the scipy layout
+ *           (cluster id, cluster id, height, size): rows offsets[b] .. offsets[b] + T_b - 2 of Z_out [N,4] belong to
+ *           recording b (one unused row per recording).
+ * The flat clusters of VBx/vbhmm.py:144-146 are fcluster(Z, -(thr + threshold), 'distance') (the `adjust` shift of
+ * :142-143 cancels); vbx_b200/ahc.py holds that O(T) traversal.  workspace: vbx_ahc_workspace_bytes() bytes of
+ * device memory (dominated by 8 * sum_b T_b^2), 256-byte aligned.  At most 65535 recordings per call. */
+int vbx_ahc_workspace_bytes(vbx_handle_t h, size_t *bytes_out);
+int vbx_ahc(vbx_handle_t h, const void *x, int32_t x_is_f64, int32_t dim, void *workspace, size_t workspace_bytes,
+            double *Z_out, double *thr_out, void *stream);
+
 /* Output step, VBx/vbhmm.py:160-162: first_out[t] = argsort(-gamma[t])[0], second_out[t] = argsort(-gamma[t])[1]
  * over the live states of the frame's recording (second_out may be NULL; -1 when the recording has one state).
  * gamma [N,S] as left by vbx_run, n_states [n_rec] or NULL, outputs int32 [N]; all device pointers. */

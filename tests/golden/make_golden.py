@@ -180,11 +180,44 @@ def es2005a_model():
                         plda_tr=wccn.T[::-1], plda_psi=acvar[::-1], sha_plda=sha(plda_f), sha_transform=sha(tr_f))
 
 
+def ahc_cases():
+    """AHC initialisation (VBx/vbhmm.py:131-146) with the reference's cos_similarity and twoGMMcalib_lin; scipy's
+    average linkage stands in for fastcluster (same algorithm).  Case 0 is ES2005a, the others are synthetic."""
+    es = np.load(os.path.join(HERE, 'es2005a.npz'))
+    cases = {'es2005a': es['x_lda']}
+    rng = np.random.default_rng(77)
+    for name, T, spk, noise in (('syn_a', 150, 3, 0.6), ('syn_b', 333, 6, 0.9), ('syn_c', 40, 2, 0.4)):
+        centres = rng.standard_normal((spk, 128))
+        who = np.repeat(rng.integers(0, spk, T // 5 + 1), 5)[:T]
+        cases[name] = ref_dl.l2_norm(centres[who] + noise * rng.standard_normal((T, 128)))
+    out = {}
+    for name, x in cases.items():
+        scr = ref_dl.cos_similarity(x)
+        thr, _ = ref_dl.twoGMMcalib_lin(scr.ravel())
+        lin = linkage(squareform(-scr, checks=False), method='average')
+        Z = lin.copy()
+        adjust = abs(lin[:, 2].min())
+        lin[:, 2] += adjust
+        labels = fcluster(lin, -(thr - 0.015) + adjust, criterion='distance') - 1
+        if name != 'es2005a':
+            out[name + '/x'] = x
+        else:
+            assert np.array_equal(labels, es['labels_ahc'])
+        out[name + '/thr'] = thr
+        out[name + '/Z'] = Z
+        out[name + '/labels'] = labels.astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, 'ahc_cases.npz'), **out)
+
+
 if __name__ == '__main__':
     np.random.seed(0)
     if sys.argv[1:] == ['model']:
         es2005a_model()
         sys.exit(0)
+    if sys.argv[1:] == ['ahc']:
+        ahc_cases()
+        sys.exit(0)
     es2005a()
     es2005a_model()
+    ahc_cases()
     synthetic_cases()

@@ -125,3 +125,22 @@ def test_es2005a_raw_xvectors_to_rttm_on_gpu(es):
     assert len(lines) == 50 and all(l.startswith('SPEAKER ES2005a 1 ') for l in lines)
     starts = np.array([float(l.split()[3]) for l in lines])
     np.testing.assert_allclose(starts, es['rttm_starts'], atol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('chain', ['tcgen05', 'float64'])
+def test_es2005a_everything_on_the_device(es, chain):
+    """Raw x-vectors -> x-vector transform / PLDA projection -> AHC initialisation (vbx_ahc) -> VB-HMM -> labels, all
+    on the B200; only the linkage matrix and the labels come back.  Equals the reference's AHC labels, final labels
+    and RTTM segmentation."""
+    m = np.load(os.path.join(GOLD, 'es2005a_model.npz'))
+    dev = torch.device('cuda:0')
+    lines, labels, g = pipeline.diarize_recording(
+        es['x_raw'], es['seg_times'], None, (m['mean1'], m['mean2'], m['lda']),
+        (m['plda_mu'], m['plda_tr'], m['plda_psi']), float(es['Fa']), float(es['Fb']), float(es['loopProb']),
+        smoothing=float(es['smoothing']), max_iters=40, epsilon=1e-6, device=dev, recording='ES2005a',
+        chain=chain, plda_is_diagonal=True, threshold=-0.015)
+    assert g.shape[1] == es['gamma'].shape[1] == 31          # same AHC speaker count and numbering
+    assert np.array_equal(labels, es['labels'])
+    assert np.abs(g.double().cpu().numpy() - es['gamma']).max() <= 5e-3
+    assert len(lines) == 50

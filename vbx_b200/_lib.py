@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get('VBX_B200_LIB', os.path.join(_HERE, 'libvbx_b200.so'))
 
 EXPORTS = ['vbx_version', 'vbx_padded_states', 'vbx_create', 'vbx_destroy', 'vbx_last_error',
            'vbx_set_option', 'vbx_plan', 'vbx_bind_workspace', 'vbx_prepare_scale',
-           'vbx_prepare_project', 'vbx_prepare_xvectors', 'vbx_run', 'vbx_hard_labels', 'vbx_launch_count', 'vbx_get_timings', 'vbx_f64_workspace_bytes',
+           'vbx_prepare_project', 'vbx_prepare_xvectors', 'vbx_run', 'vbx_hard_labels', 'vbx_ahc_workspace_bytes', 'vbx_ahc', 'vbx_launch_count', 'vbx_get_timings', 'vbx_f64_workspace_bytes',
            'vbx_run_f64']
 
 FLAG_NONFINITE, FLAG_ELBO_DECREASED, FLAG_CONVERGED = 1, 2, 4
@@ -55,6 +55,10 @@ def load():
     lib.vbx_prepare_scale.argtypes = [vp, vp, vp, vp, vp]
     lib.vbx_prepare_project.restype = ctypes.c_int
     lib.vbx_prepare_project.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    lib.vbx_ahc_workspace_bytes.restype = ctypes.c_int
+    lib.vbx_ahc_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    lib.vbx_ahc.restype = ctypes.c_int
+    lib.vbx_ahc.argtypes = [vp, vp, i32, i32, vp, ctypes.c_size_t, vp, vp, vp]
     lib.vbx_hard_labels.restype = ctypes.c_int
     lib.vbx_hard_labels.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.vbx_prepare_xvectors.restype = ctypes.c_int

@@ -22,6 +22,9 @@ struct vbx_handle_s {
     int opt_timing = 0;
     int opt_gemm = 0;  // 0 = mma.sync 3xTF32, 1 = FFMA
     int64_t launches = 0;
+    std::vector<int64_t> offsets_host;  // kept for the AHC workspace layout
+    std::vector<int64_t> ahc_d_off;
+    size_t ahc_need = 0;
     // per-kernel-class CUDA-event timing (opt_timing): events are recorded on the launching stream
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -275,6 +278,9 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
     pl.lchunk_rec = reinterpret_cast<const int32_t *>(base + o_lcr);
     pl.lchunk_idx = reinterpret_cast<const int32_t *>(base + o_lci);
     h->ws_need = carve(pl, nullptr, nullptr);
+    h->offsets_host.assign(offsets_host, offsets_host + (n_rec ? n_rec + 1 : 0));
+    if (n_rec == 0) h->offsets_host.assign(1, 0);
+    h->ahc_need = vbx::ahc_workspace_bytes(h->offsets_host.data(), n_rec, &h->ahc_d_off);
     h->planned = true;
     if (workspace_bytes_out) *workspace_bytes_out = h->ws_need;
     return VBX_OK;
@@ -466,6 +472,30 @@ int vbx_hard_labels(vbx_handle_t h, const float *gamma, const int32_t *n_states,
     if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_hard_labels: call vbx_plan first");
     if (h->plan.n_frames && (!gamma || !first_out)) return fail(h, VBX_ERR_ARG, "vbx_hard_labels: null pointer");
     return counted(h, vbx::launch_hard_labels(h->plan, gamma, n_states, first_out, second_out, (cudaStream_t)stream), "hard_labels");
+}
+
+int vbx_ahc_workspace_bytes(vbx_handle_t h, size_t *bytes_out) {
+    if (!h || !bytes_out) return VBX_ERR_ARG;
+    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_ahc_workspace_bytes: call vbx_plan first");
+    *bytes_out = h->ahc_need;
+    return VBX_OK;
+}
+
+int vbx_ahc(vbx_handle_t h, const void *x, int32_t x_is_f64, int32_t dim, void *workspace, size_t workspace_bytes,
+            double *Z_out, double *thr_out, void *stream) {
+    if (!h) return VBX_ERR_ARG;
+    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_ahc: call vbx_plan first");
+    if (dim < 1) return fail(h, VBX_ERR_ARG, "vbx_ahc: dim < 1");
+    if (h->plan.n_rec == 0) return VBX_OK;
+    if (!workspace || !thr_out || (h->plan.n_frames && (!x || !Z_out))) return fail(h, VBX_ERR_ARG, "vbx_ahc: null pointer");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(h, VBX_ERR_ARG, "vbx_ahc: workspace must be 256-byte aligned");
+    if (workspace_bytes < h->ahc_need) return fail(h, VBX_ERR_ARG, "vbx_ahc: workspace smaller than vbx_ahc_workspace_bytes()");
+    std::string why;
+    int n = vbx::launch_ahc(h->plan, h->ahc_d_off, x, x_is_f64, dim, workspace, workspace_bytes, Z_out, thr_out,
+                            (cudaStream_t)stream, &why);
+    if (n < 0) return fail(h, VBX_ERR_CUDA, "vbx_ahc: " + why);
+    h->launches += n;
+    return VBX_OK;
 }
 
 int vbx_f64_workspace_bytes(vbx_handle_t h, size_t *bytes_out) {

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #define VBX_EPS_TR 1e-8f  // additive floor inside the HMM logs of the reference, VBx/VBx.py:158
 
@@ -171,6 +172,10 @@ int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const dou
                    cudaStream_t st);
 int launch_hard_labels(const Plan &pl, const float *gamma, const int32_t *n_states, int32_t *first, int32_t *second,
                        cudaStream_t st);
+// AHC initialisation (vbx_ahc.cu)
+size_t ahc_workspace_bytes(const int64_t *offsets_host, int n_rec, std::vector<int64_t> *d_off_host);
+int launch_ahc(const Plan &pl, const std::vector<int64_t> &d_off, const void *x, int x_is_f64, int dim, void *workspace,
+               size_t workspace_bytes, double *Z_out, double *thr_out, cudaStream_t st, std::string *err);
 // tcgen05 projection (vbx_project_tc.cu)
 int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, const float *Phi, float *rho,
                            float *gframe, cudaStream_t st, std::string *err);

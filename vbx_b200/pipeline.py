@@ -81,39 +81,52 @@ def rttm_lines(recording, starts, ends, labels):
 
 def diarize_recording(x_raw, seg_times, ahc_labels, transform, plda, Fa, Fb, loopP, lda_dim=128, smoothing=5.0,
                       max_iters=40, epsilon=1e-6, device=None, recording='rec', chain='tcgen05',
-                      plda_is_diagonal=False):
-    """One recording end to end on the device, the AHC+VB branch of VBx/vbhmm.py:120-172 given the AHC labels.
+                      plda_is_diagonal=False, threshold=-0.015):
+    """One recording end to end on the device, the AHC+VB branch of VBx/vbhmm.py:120-172.
     transform = (mean1, mean2, lda); plda = (mu, tr, psi) as read from the Kaldi model (diagonalised here as in
     VBx/vbhmm.py:136-143 unless plda_is_diagonal says it already is).
+    ahc_labels=None runs the AHC initialisation on the device too (vbx_ahc, VBx/vbhmm.py:131-146, `threshold` is
+    the --threshold bias); otherwise the given labels seed gamma.
     chain='tcgen05' runs the x-vector transform and the PLDA projection in the fused tensor-core kernels
     (vbx_prepare_xvectors; needs lda_dim == 128 and a raw dimension that is a multiple of 32), chain='float64'
     evaluates them with float64 torch ops on the device.  Returns (rttm lines, labels, gamma)."""
     from .batch import VbxBatch
+    from . import ahc as _ahc
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
     f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
     f32 = lambda a: f64(a).float().contiguous()
     mu, tr, psi = plda if plda_is_diagonal else diagonalise_plda(*plda)
+    T = int(np.asarray(x_raw).shape[0])
+    if chain not in ('tcgen05', 'float64'):
+        raise ValueError("chain must be 'tcgen05' or 'float64'")
+    if chain == 'tcgen05' and (lda_dim != 128 or tr.shape[0] != 128):
+        raise ValueError("chain='tcgen05' needs a 128-dimensional PLDA space")
+    # the front end does not depend on the number of speakers: run it on a planning-only batch first
+    front = VbxBatch([T], lda_dim, 1, device=dev)
+    if chain == 'tcgen05':
+        mean1, mean2, lda = transform
+        rho, x = front.prepare_xvectors(f32(x_raw), f32(mean1), f32(lda), f32(mean2), f32(mu), f32(tr), f32(psi))
+        Phi = f32(psi)
+    else:
+        mean1, mean2, lda = (f64(a) for a in transform)
+        x = xvector_transform(f64(x_raw), mean1, mean2, lda).contiguous()
+        fea = plda_project(x, f64(mu), f64(tr), lda_dim)
+        Phi = f64(psi[:lda_dim]).float()
+        rho = None
+    if ahc_labels is None:
+        ahc_labels = _ahc.ahc_batch(front, x, threshold=threshold)[0][0]
+    front.close()
     S = int(np.max(ahc_labels)) + 1
     q0 = soft_init(torch.from_numpy(np.asarray(ahc_labels)).to(dev), S, smoothing)
-    T = int(np.asarray(x_raw).shape[0])
     vb = VbxBatch([T], lda_dim, S, device=dev)
     vb.set_option('gemm', 1)
     g = torch.zeros((T, vb.S), dtype=torch.float32, device=dev)
     g[:, :S] = q0
     p = torch.zeros((1, vb.S), dtype=torch.float32, device=dev)
     p[0, :S] = 1.0 / S
-    if chain == 'tcgen05':
-        if lda_dim != 128 or tr.shape[0] != 128:
-            raise ValueError("chain='tcgen05' needs a 128-dimensional PLDA space")
-        mean1, mean2, lda = transform
-        vb.prepare_xvectors(f32(x_raw), f32(mean1), f32(lda), f32(mean2), f32(mu), f32(tr), f32(psi))
-    elif chain == 'float64':
-        mean1, mean2, lda = (f64(a) for a in transform)
-        x = xvector_transform(f64(x_raw), mean1, mean2, lda)
-        fea = plda_project(x, f64(mu), f64(tr), lda_dim)
-        vb.prepare_scale(fea.float().contiguous(), f64(psi[:lda_dim]).float())
-    else:
-        raise ValueError("chain must be 'tcgen05' or 'float64'")
+    if rho is not None:       # the speaker count was not known when the front end ran: hand its features to the new plan
+        fea = rho / torch.sqrt(Phi)[None, :]
+    vb.prepare_scale(fea.float().contiguous(), Phi)
     vb.run(g, p, Fa=Fa, Fb=Fb, loopProb=loopP, maxIters=max_iters, epsilon=epsilon)
     labels = vb.hard_labels(g).cpu().numpy().astype(np.int64)      # only the labels leave the device
     s, e, l = merge_adjacent_labels(seg_times[:, 0], seg_times[:, 1], labels)
