@@ -270,6 +270,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--fb-spl', type=int, default=0)
     ap.add_argument('--projection', type=int, default=0)
+    ap.add_argument('--fb-classic', type=int, default=0, help='1 = normalise-every-frame forward-backward sweep (A/B against the look-ahead kernel)')
     ap.add_argument('--front', default='project', choices=['project', 'xvectors'],
                     help="what feeds the EM loop: 'project' = rho = X.V (the headline definition, SURVEY 8d); 'xvectors' = the "
                          "real-data chain vbx_prepare_xvectors (x-vector transform + PLDA projection, two tcgen05 passes)")
@@ -311,6 +312,8 @@ def main():
             vb.set_option('fb_states_per_lane', args.fb_spl)
         if args.projection:
             vb.set_option('projection', args.projection)
+        if args.fb_classic:
+            vb.set_option('fb_classic', 1)
         vb.set_option('timing', 1)
         S = vb.S
         rho = torch.empty((N, R_DIM), dtype=torch.float32, device=device)

@@ -58,7 +58,8 @@ int vbx_create(int32_t device, vbx_handle_t *out);
 int vbx_destroy(vbx_handle_t h);
 const char *vbx_last_error(vbx_handle_t h);
 
-/* Tuning knobs (ints): "fb_states_per_lane" (0 = auto, 1, 2, 4), "projection" (0 = auto, 1 = FFMA tiles,
+/* Tuning knobs (ints): "fb_states_per_lane" (0 = auto, 1, 2, 4), "fb_classic" (forward-backward sweep: 0 = one-step
+ * look-ahead recurrences, 1 = normalise-every-frame), "projection" (0 = auto, 1 = FFMA tiles,
  * 2 = tcgen05 3xTF32), "gemm" (in-loop contractions: 0 = tensor cores in split-precision 3xTF32, 1 = FFMA),
  * "timing" (0/1, see vbx_get_timings).  Unknown names return VBX_ERR_ARG. */
 int vbx_set_option(vbx_handle_t h, const char *name, int32_t value);

@@ -18,6 +18,7 @@ struct vbx_handle_s {
     size_t ws_need = 0;
     void *plan_mem = nullptr;  // one device allocation backing all plan arrays
     int opt_fb_spl = 0;
+    int opt_fb_classic = 0;  // 1 = the normalise-every-frame sweep, 0 = one-step look-ahead
     int opt_projection = 0;
     int opt_timing = 0;
     int opt_gemm = 0;  // 0 = mma.sync 3xTF32, 1 = FFMA
@@ -139,6 +140,10 @@ int vbx_set_option(vbx_handle_t h, const char *name, int32_t value) {
     if (!strcmp(name, "fb_states_per_lane")) {
         if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, VBX_ERR_ARG, "fb_states_per_lane must be 0,1,2,4");
         h->opt_fb_spl = value;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "fb_classic")) {
+        h->opt_fb_classic = value ? 1 : 0;
         return VBX_OK;
     }
     if (!strcmp(name, "gemm")) {
@@ -459,7 +464,7 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
         if (rc) return rc;
         {
             Timed t(h, st, VBX_K_FWDBWD);
-            rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, st), "forward_backward");
+            rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, h->opt_fb_classic, st), "forward_backward");
         }
         if (rc) return rc;
     }

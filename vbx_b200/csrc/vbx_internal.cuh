@@ -157,7 +157,7 @@ int launch_speaker_model(const Plan &pl, const Workspace &ws, const RunParams &r
 int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st);
 int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
-                            int spl, cudaStream_t st);
+                            int spl, int classic, cudaStream_t st);
 // chunked-scan forward-backward for long recordings (vbx_long_kernels.cu)
 int launch_forward_backward_long(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                                  const int32_t *n_states, cudaStream_t st);

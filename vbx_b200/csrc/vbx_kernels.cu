@@ -633,6 +633,48 @@ int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStr
 // load turns into load+select and stalls on the spot); the main loops carry no per-group predicates, only the
 // ragged tail does; the reciprocal is a single MUFU.RCP.
 // ------------------------------------------------------------------------------------------------
+#ifndef VBX_LDO
+#define VBX_LDO "ld.volatile.global"
+#define VBX_STO "st.volatile.global"
+#endif
+// Ordered prefetch loads: ptxas sinks plain (reorderable) LDGs of a burst towards their first use, which shrinks the
+// prefetch window; volatile accesses keep their program order, so a burst issued before the first volatile store of
+// a chunk stays there.
+template <int N>
+__device__ __forceinline__ Vec<N> ldo_vec(const float *p);
+template <>
+__device__ __forceinline__ Vec<1> ldo_vec<1>(const float *p) {
+    Vec<1> r;
+    asm volatile(VBX_LDO ".f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p) : "memory");
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<2> ldo_vec<2>(const float *p) {
+    Vec<2> r;
+    asm volatile(VBX_LDO ".v2.f32 {%0, %1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p) : "memory");
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<4> ldo_vec<4>(const float *p) {
+    Vec<4> r;
+    asm volatile(VBX_LDO ".v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p) : "memory");
+    return r;
+}
+template <int N>
+__device__ __forceinline__ void sto_vec(float *p, const float *v);
+template <>
+__device__ __forceinline__ void sto_vec<1>(float *p, const float *v) {
+    asm volatile(VBX_STO ".f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
+}
+template <>
+__device__ __forceinline__ void sto_vec<2>(float *p, const float *v) {
+    asm volatile(VBX_STO ".v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+}
+template <>
+__device__ __forceinline__ void sto_vec<4>(float *p, const float *v) {
+    asm volatile(VBX_STO ".v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -712,7 +754,7 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
                     a[k] = an[k];
                     base[k] = fmaf(P, an[k], w[k]);
                 }
-                st_vec<SPL>(ga + t * gstr, an);
+                sto_vec<SPL>(ga + t * gstr, an);
                 if (l == 0) rs[t * rstr] = r;
             } else {
                 const bool act = t < T;
@@ -722,7 +764,7 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
                     base[k] = act ? fmaf(P, an[k], w[k]) : base[k];
                 }
                 if (act) {
-                    st_vec<SPL>(ga + t * gstr, an);
+                    sto_vec<SPL>(ga + t * gstr, an);
                     if (l == 0) rs[t * rstr] = r;
                 }
             }
@@ -730,7 +772,7 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
         // one chunk = PF frames: first issue the burst of loads for the NEXT chunk, then run this chunk's steps
         auto fchunk = [&](const int t0, Vec<SPL>(&cur)[PF], Vec<SPL>(&nxt)[PF], const bool check) {
 #pragma unroll
-            for (int i = 0; i < PF; ++i) nxt[i] = ldg_vec<SPL>(pp + (int64_t)min(t0 + PF + i, Tlast) * S_PAD);
+            for (int i = 0; i < PF; ++i) nxt[i] = ldo_vec<SPL>(pp + (int64_t)min(t0 + PF + i, Tlast) * S_PAD);
 #pragma unroll
             for (int i = 0; i < PF; ++i) fstep(t0 + i, cur[i], check);
         };
@@ -770,9 +812,9 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
             const int t = max(T - 2 - ii, 0);
             const int t1 = min(t + 1, Tlast);
             Slot sl;
-            sl.p = ldg_vec<SPL>(pp + (int64_t)t1 * S_PAD);
-            sl.a = ld_vec<SPL>(ga + t * gstr);
-            sl.r = rs[t1 * rstr];
+            sl.p = ldo_vec<SPL>(pp + (int64_t)t1 * S_PAD);
+            sl.a = ldo_vec<SPL>(ga + t * gstr);
+            sl.r = ldo_vec<1>(rs + t1 * rstr).v[0];
             return sl;
         };
         auto bstep = [&](const int ii, const Slot &c, const bool check) {
@@ -804,7 +846,7 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
                     occf[k] += gn[k];
                     entf[k] += u[k];
                 }
-                st_vec<SPL>(ga + t * gstr, gn);
+                sto_vec<SPL>(ga + t * gstr, gn);
             } else {
                 const bool act = t >= 0;
 #pragma unroll
@@ -814,7 +856,7 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
                     occf[k] += act ? gn[k] : 0.f;
                     entf[k] += act ? u[k] : 0.f;
                 }
-                if (act) st_vec<SPL>(ga + t * gstr, gn);
+                if (act) sto_vec<SPL>(ga + t * gstr, gn);
             }
         };
         auto bchunk = [&](const int i0, Slot(&cur)[PB], Slot(&nxt)[PB], const bool check) {
@@ -862,13 +904,318 @@ __global__ void __launch_bounds__(128) forward_backward_kernel(Plan pl, Workspac
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward-backward with one step of look-ahead: the group reduction leaves the per-frame dependency chain.
+//
+// The kernel above needs  sigma_t = sum_i p_t,i (P a_{t-1,i} + w_i)  before it can touch frame t+1: a multiply, a
+// 3-level shuffle reduction, a reciprocal and two more multiplies, ~125 cycles per frame with nothing else to do
+// (at most 7 warps per SM exist for 4096 recordings).  Here the forward vector is carried with a lagging scale,
+//     y_{t+1} = r_{t+1} p_{t+1} o (P y_t + w Y_t),      Y_t = sum_i y_t,i,
+// and Y is advanced by a scalar recurrence fed by a reduction that only needs the PREVIOUS vector:
+//     Y_{t+1} = r_{t+1} (P q_t + c_{t+1} Y_t),   q_t = p_{t+1} . y_t,   c_{t+1} = p_{t+1} . w   (c does not depend on y).
+// q_t is launched as soon as y_t exists and is consumed one frame later, so two frames share one reduction latency
+// and the reductions for c fill the gaps.  r_{t+1} = 1/sigma_{t-1} keeps Y_t = sigma_t sigma_{t-1} (no under/overflow:
+// sigma >= ~1e-8).  Outputs are unchanged: a_t = y_t / Y_t,  1/sigma_t = r_t Y_{t-1} / Y_t.
+// Backward, same idea:  v_t = kappa_{t+1} o b_{t+1} (kappa_t = p_t / sigma_t),  b_t = P v_t + d_t,
+//     d_t = w . v_t = P e_{t+1} + d_{t+1} f_{t+1},   e_{t+1} = (w o kappa_{t+1}) . v_{t+1},   f_{t+1} = w . kappa_{t+1}.
+// ------------------------------------------------------------------------------------------------
+template <int S_PAD, int SPL>
+__global__ void __launch_bounds__(128) forward_backward_la_kernel(Plan pl, Workspace ws, RunParams rp, float *gamma,
+                                                                  float *pi_io, const int32_t *__restrict__ n_states) {
+    constexpr int LPR = S_PAD / SPL;
+    constexpr int RPW = 32 / LPR;
+    // Ping-pong register bursts (see the kernel above): one burst must cover the DRAM latency under load, and the
+    // look-ahead steps are about half as long as the normalise-every-frame ones, so the bursts are deeper.
+    constexpr int PF = (SPL == 4) ? 10 : (SPL == 2 ? 24 : 32); // frames per prefetch burst, forward sweep
+    constexpr int PB = (SPL == 4) ? 5 : (SPL == 2 ? 10 : 16);  // ... backward sweep (three arrays per frame)
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int g = lane / LPR, l = lane % LPR;
+    const int slot = warp_global * RPW + g;
+    int rec = -1;
+    if (slot < pl.n_rec) rec = pl.order[slot];
+    const bool live = rec >= 0 && ws.active[rec] != 0 && pl.lrec_nchunks[rec] == 0;
+    int64_t f0 = 0;
+    int T = 0;
+    if (live) {
+        f0 = pl.offsets[rec];
+        T = (int)(pl.offsets[rec + 1] - f0);
+    }
+    int Tmax = T, Tmin = live ? T : 0x7fffffff;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, off));
+        Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, off));
+    }
+    if (Tmax == 0) return;  // warp-uniform: no live recording in this warp
+    const int Tlast = max(T - 1, 0);
+    const int ns = live ? (n_states ? n_states[rec] : S_PAD) : 0;
+    const float P = rp.loopP, Q = 1.f - rp.loopP;
+
+    float pi[SPL], w[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int s = l * SPL + k;
+        const bool sl = live && s < ns;
+        pi[k] = sl ? pi_io[(int64_t)rec * S_PAD + s] : 0.f;
+        w[k] = sl ? fmaf(Q, pi[k], VBX_EPS_TR) : 0.f;   // VBx/VBx.py:98,159
+    }
+    const float *pp = ws.p + f0 * S_PAD + l * SPL;
+    float *ga = live ? gamma + f0 * S_PAD + l * SPL : ws.scratch + l * SPL;
+    float *rs = live ? ws.rsigma + f0 : ws.scratch + kMaxS;
+    const int64_t gstr = live ? S_PAD : 0;
+    const int rstr = live ? 1 : 0;
+
+    // ---------------- forward sweep, VBx/VBx.py:164,167-168 ----------------
+    float alast[SPL];                       // forward variable of the recording's last frame
+    {
+        // frame 0: y_0 = p_0 o (pi + eps)  (VBx/VBx.py:164), normalised directly
+        float y[SPL];
+        const Vec<SPL> p0 = ldg_vec<SPL>(pp);
+        const Vec<SPL> p1 = ldg_vec<SPL>(pp + (int64_t)min(1, Tlast) * S_PAD);
+        float loc = 0.f, locq = 0.f, locc = 0.f;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int s = l * SPL + k;
+            y[k] = (live && s < ns) ? p0.v[k] * (pi[k] + VBX_EPS_TR) : 0.f;
+            loc += y[k];
+            locq = fmaf(p1.v[k], y[k], locq);
+            locc = fmaf(p1.v[k], w[k], locc);
+        }
+        float Yc = group_sum<LPR>(loc);     // Y_0 = sigma_0
+        float q = group_sum<LPR>(locq);     // q_0 = p_1 . y_0
+        float c = group_sum<LPR>(locc);     // c_1 = p_1 . w
+        float rn = 1.f;                     // r_1
+        float rs1 = rcp_fast(Yc);           // 1/sigma_0 (becomes r_2)
+        {
+            float an[SPL];
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                an[k] = y[k] * rs1;
+                alast[k] = an[k];
+            }
+            st_vec<SPL>(ga, an);
+            if (l == 0) rs[0] = rs1;
+        }
+        // step j handles frame s = j + 1 with ps = p_s (slot j) and pn = p_{s+1} (slot j + 1)
+        auto fstep = [&](const int j, const Vec<SPL> &ps, const Vec<SPL> &pn, const bool check) {
+            const int s = j + 1;
+            float ys[SPL], locq = 0.f, locc = 0.f;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                ys[k] = (rn * ps.v[k]) * fmaf(P, y[k], w[k] * Yc);
+                locq = fmaf(pn.v[k], ys[k], locq);
+                locc = fmaf(pn.v[k], w[k], locc);
+            }
+            const float qn = group_sum<LPR>(locq);              // consumed by the NEXT step
+            const float cn = group_sum<LPR>(locc);
+            const float Ys = rn * fmaf(P, q, c * Yc);           // Y_s = sum_i y_s,i
+            const float inv = rcp_fast(Ys);
+            const float rsig = rn * Yc * inv;                   // 1 / sigma_s
+            float an[SPL];
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                an[k] = ys[k] * inv;
+                y[k] = ys[k];
+            }
+            Yc = Ys;
+            q = qn;
+            c = cn;
+            rn = rs1;
+            rs1 = rsig;
+            if (!check) {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) alast[k] = an[k];
+                sto_vec<SPL>(ga + s * gstr, an);
+                if (l == 0) rs[s * rstr] = rsig;
+            } else {
+                const bool act = s < T;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) alast[k] = act ? an[k] : alast[k];
+                if (act) {
+                    sto_vec<SPL>(ga + s * gstr, an);
+                    if (l == 0) rs[s * rstr] = rsig;
+                }
+            }
+        };
+        Vec<SPL> bufA[PF], bufB[PF];
+        Vec<SPL> ps = p1;                   // row of frame 1
+        // slot i of a burst starting at step j0 holds the row of frame j0 + i + 2 (`pn` of step j0 + i)
+        auto fchunk = [&](const int j0, Vec<SPL>(&cur)[PF], Vec<SPL>(&nxt)[PF], const bool check) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) nxt[i] = ldo_vec<SPL>(pp + (int64_t)min(j0 + PF + i + 2, Tlast) * S_PAD);
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                fstep(j0 + i, ps, cur[i], check);
+                ps = cur[i];
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < PF; ++i) bufA[i] = ldg_vec<SPL>(pp + (int64_t)min(i + 2, Tlast) * S_PAD);
+        int j0 = 0;
+        for (; j0 + 2 * PF <= Tmin - 1; j0 += 2 * PF) {
+            fchunk(j0, bufA, bufB, false);
+            fchunk(j0 + PF, bufB, bufA, false);
+        }
+        for (; j0 < Tmax - 1; j0 += 2 * PF) {
+            fchunk(j0, bufA, bufB, true);
+            fchunk(j0 + PF, bufB, bufA, true);
+        }
+    }
+    __syncwarp();  // rsigma written by lane l==0 of each group is read by the whole group below
+
+    // ---------------- backward sweep, VBx/VBx.py:165,170-171,174 + eq. (24) statistics ----------------
+    float g0[SPL], occf[SPL], entf[SPL];
+    double enter[SPL], occ[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        g0[k] = alast[k];        // gamma_{T-1} = forward variable (already stored)
+        occ[k] = (double)alast[k];
+        enter[k] = 0.0;
+        occf[k] = 0.f;
+        entf[k] = 0.f;
+    }
+    {
+        struct Slot {             // data of backward step ii (frame t = T-2-ii): p_{t+1}, 1/sigma_{t+1}, a_t
+            Vec<SPL> p, a;
+            float r;
+        };
+        auto load_slot = [&](const int ii) {
+            const int t = max(T - 2 - ii, 0);
+            const int t1 = min(t + 1, Tlast);
+            Slot sl;
+            sl.p = ldo_vec<SPL>(pp + (int64_t)t1 * S_PAD);
+            sl.a = ldo_vec<SPL>(ga + t * gstr);
+            sl.r = ldo_vec<1>(rs + t1 * rstr).v[0];
+            return sl;
+        };
+        Slot bufA[PB], bufB[PB];
+        Slot cur = load_slot(0);
+#pragma unroll
+        for (int i = 0; i < PB; ++i) bufA[i] = load_slot(i + 1);       // slot i of a burst at i0 = data of step i0 + i + 1
+        // state entering step ii: b = b_{t+1}, dprev = d_{t+1}, e = e_{t+1}, kap = kappa_{t+1}, f = f_{t+1}
+        // (b_{T-1} = 1 = P * 0 + 1, i.e. v_{T-1} = 0, d_{T-1} = 1, e_{T-1} = 0)
+        float b[SPL], kap[SPL];
+        float dprev = 1.f, e = 0.f, f;
+        {
+            float locf = 0.f;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                b[k] = 1.f;
+                kap[k] = cur.p.v[k] * cur.r;
+                locf = fmaf(w[k], kap[k], locf);
+            }
+            f = group_sum<LPR>(locf);
+        }
+        auto bstep = [&](const int ii, const Slot &c, const Slot &nx, const bool check) {
+            const int t = T - 2 - ii;
+            float v[SPL], kapn[SPL], loce = 0.f, locf = 0.f;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                v[k] = kap[k] * b[k];                               // v_t = p_{t+1} b_{t+1} / sigma_{t+1}
+                kapn[k] = nx.p.v[k] * nx.r;                          // kappa_t
+                const float wk = w[k] * kapn[k];
+                loce = fmaf(wk, v[k], loce);
+                locf += wk;
+            }
+            const float en = group_sum<LPR>(loce);                   // e_t, consumed by the NEXT step
+            const float fn = group_sum<LPR>(locf);                   // f_t
+            const float d = fmaf(P, e, dprev * f);                   // d_t = w . v_t
+            float gn[SPL], bn[SPL], gs = 0.f;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                bn[k] = fmaf(P, v[k], d);
+                gn[k] = c.a.v[k] * bn[k];
+                gs += gn[k];
+            }
+            {   // rows of gamma sum to one (removes the common-mode rounding drift)
+                const float sc = rcp_fast(group_sum<LPR>(gs));
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) gn[k] *= sc;
+            }
+            if (!check) {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    g0[k] = gn[k];
+                    occf[k] += gn[k];
+                    entf[k] += v[k];
+                }
+                sto_vec<SPL>(ga + t * gstr, gn);
+            } else {
+                const bool act = t >= 0;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    g0[k] = act ? gn[k] : g0[k];
+                    occf[k] += act ? gn[k] : 0.f;
+                    entf[k] += act ? v[k] : 0.f;
+                }
+                if (act) sto_vec<SPL>(ga + t * gstr, gn);
+            }
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                b[k] = bn[k];
+                kap[k] = kapn[k];
+            }
+            dprev = d;
+            e = en;
+            f = fn;
+        };
+        auto bchunk = [&](const int i0, Slot(&cb)[PB], Slot(&nb)[PB], const bool check) {
+#pragma unroll
+            for (int i = 0; i < PB; ++i) nb[i] = load_slot(i0 + PB + i + 1);
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                bstep(i0 + i, cur, cb[i], check);
+                cur = cb[i];
+            }
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                occ[k] += (double)occf[k];
+                enter[k] += (double)entf[k];
+                occf[k] = 0.f;
+                entf[k] = 0.f;
+            }
+        };
+        int i0 = 0;
+        for (; i0 + 2 * PB <= Tmin - 1; i0 += 2 * PB) {
+            bchunk(i0, bufA, bufB, false);
+            bchunk(i0 + PB, bufB, bufA, false);
+        }
+        for (; i0 < Tmax - 1; i0 += 2 * PB) {
+            bchunk(i0, bufA, bufB, true);
+            bchunk(i0 + PB, bufB, bufA, true);
+        }
+    }
+
+    // ---------------- tail: eq. (24), VBx/VBx.py:101-104 ----------------
+    double pn[SPL];
+    float loc = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        pn[k] = (double)g0[k] + (double)Q * (double)pi[k] * enter[k];
+        loc += (float)pn[k];
+    }
+    const float tot = group_sum<LPR>(loc);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int s = l * SPL + k;
+            pi_io[(int64_t)rec * S_PAD + s] = (float)(pn[k] / (double)tot);
+            ws.occ[(int64_t)rec * S_PAD + s] = (float)occ[k];
+        }
+    }
+}
+
 template <int S_PAD, int SPL>
 static int launch_fb_t(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
-                       const int32_t *n_states, cudaStream_t st) {
+                       const int32_t *n_states, bool classic, cudaStream_t st) {
     constexpr int RPW = 32 / (S_PAD / SPL);
     const int warps = (pl.n_rec + RPW - 1) / RPW;
     const int blocks = (warps + 3) / 4;
-    forward_backward_kernel<S_PAD, SPL, true><<<blocks, 128, 0, st>>>(pl, ws, rp, gamma, pi, n_states);
+    if (classic)
+        forward_backward_kernel<S_PAD, SPL, true><<<blocks, 128, 0, st>>>(pl, ws, rp, gamma, pi, n_states);
+    else
+        forward_backward_la_kernel<S_PAD, SPL><<<blocks, 128, 0, st>>>(pl, ws, rp, gamma, pi, n_states);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -915,10 +1262,10 @@ __global__ void __launch_bounds__(128) elbo_kernel(Plan pl, Workspace ws, RunPar
 
 int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
-                            int spl, cudaStream_t st) {
+                            int spl, int classic, cudaStream_t st) {
     if (pl.n_rec == 0) return 0;
     int rc = -1;
-#define VBX_FB(S_, L_) rc = launch_fb_t<S_, L_>(pl, ws, rp, gamma, pi, n_states, st)
+#define VBX_FB(S_, L_) rc = launch_fb_t<S_, L_>(pl, ws, rp, gamma, pi, n_states, classic != 0, st)
     const int S = pl.S;
     if (spl == 0) spl = (S >= 16) ? 2 : 1;
     if (S == 64 && spl < 2) spl = 2;
