@@ -528,7 +528,20 @@ def test_c_abi_argument_errors():
     assert lib.vbx_run(h, None, None, None, None, None, 1.0, 1.0, 0.9, 1, 0.0, None, None, 0, None, None, None, None) == -3
     assert lib.vbx_plan(h, po, 1, 128, 16, ctypes.byref(need)) == 0 and need.value > 0
     assert lib.vbx_bind_workspace(h, None, 0) == -3
+    # entry points added with the section-8f rows: state and argument checks before anything is launched
+    assert lib.vbx_set_option(h, b'fb_classic', 1) == 0 and lib.vbx_set_option(h, b'no_such_knob', 1) == -1
+    assert lib.vbx_prepare_xvectors(h, None, 256, None, None, None, None, None, None, None, None, None) == -3   # no workspace
+    assert lib.vbx_hard_labels(h, None, None, None, None, None) == -1                                          # null pointers
+    ahc_need = ctypes.c_size_t()
+    assert lib.vbx_ahc_workspace_bytes(h, ctypes.byref(ahc_need)) == 0 and ahc_need.value >= 10 * 10 * 8
+    assert lib.vbx_ahc(h, None, 0, 128, None, 0, None, None, None) == -1
+    assert lib.vbx_ahc(h, None, 0, 0, None, 0, None, None, None) == -1 and b'dim' in lib.vbx_last_error(h)
     assert lib.vbx_destroy(h) == 0
+    h2 = ctypes.c_void_p()
+    assert lib.vbx_create(0, ctypes.byref(h2)) == 0
+    assert lib.vbx_ahc_workspace_bytes(h2, ctypes.byref(ahc_need)) == -3      # not planned yet
+    assert lib.vbx_hard_labels(h2, None, None, None, None, None) == -3
+    assert lib.vbx_destroy(h2) == 0
 
 
 def test_float64_mode_ragged_batch_vs_oracle():
