@@ -15,6 +15,7 @@
 //                        O(T) work: block argmin over nnd, Lance-Williams update of one row/column, and a warp-per-row
 //                        recomputation of the few rows whose nearest neighbour was merged away.
 #include <cfloat>
+#include <climits>
 
 #include "vbx_internal.cuh"
 
@@ -255,6 +256,11 @@ __global__ void __launch_bounds__(kLinkThreads) ahc_linkage_kernel(const int64_t
             }
         }
         __syncthreads();
+        if (s_best.i == INT_MAX) {
+            // no finite distance left (NaN x-vectors): there is nothing to merge by; mark the rest of the linkage and stop
+            for (int k = step * 4 + tid; k < (T - 1) * 4; k += kLinkThreads) Z[k] = nan("");
+            return;                                               // block-uniform: s_best lives in shared memory
+        }
         const int p = s_best.i, q = r.nn[p];
         const int a = min(p, q), b = max(p, q);                  // slot a keeps the merged cluster, slot b dies
         const double dist = s_best.d;
