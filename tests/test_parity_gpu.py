@@ -46,7 +46,7 @@ def load_cases():
 CASES = load_cases()
 
 
-def run_gpu(fea, Phi, lengths, gamma0, pi0=None, n_states=None, spl=0, gemm=0, **kw):
+def run_gpu(fea, Phi, lengths, gamma0, pi0=None, n_states=None, spl=0, gemm=0, fb_classic=0, **kw):
     from vbx_b200.batch import VbxBatch
     import vbx_b200._lib as L
     lengths = np.asarray(lengths)
@@ -56,6 +56,7 @@ def run_gpu(fea, Phi, lengths, gamma0, pi0=None, n_states=None, spl=0, gemm=0, *
     if spl:
         vb.set_option('fb_states_per_lane', spl)
     vb.set_option('gemm', gemm)
+    vb.set_option('fb_classic', fb_classic)
     S = vb.S
     g = torch.zeros((fea.shape[0], S), device=dev())
     g[:, :S_user] = cuda(gamma0)
@@ -176,6 +177,21 @@ def test_ragged_batch_vs_oracle(spl):
     assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
     check_elbo(out['Li'], ref['Li'])
     assert np.all(out['n_iters'] == 8)
+
+
+@pytest.mark.parametrize('tag', ['ami_hp', 'dead_speaker', 'loop0', 'loop1', 't1', 's64', 'dihard_hp'])
+def test_classic_forward_backward_sweep(tag):
+    """The normalise-every-frame sweep (option fb_classic = 1) stays selectable for A/B runs: it meets the same goldens
+    and the two sweeps agree with each other far inside the parity bar."""
+    c = CASES[tag]
+    T = c['fea'].shape[0]
+    kw = dict(Fa=float(c['Fa']), Fb=float(c['Fb']), loopProb=float(c['loopProb']), maxIters=len(c['Li']), epsilon=-np.inf)
+    classic, ahead = (run_gpu(c['fea'], c['Phi'], [T], c['gamma0'], pi0=c['pi0'], fb_classic=v, **kw) for v in (1, 0))
+    assert np.abs(classic['gamma'] - c['gamma']).max() <= G_TOL * np.abs(c['gamma']).max()
+    assert np.abs(classic['pi'][0] - c['pi']).max() <= PI_TOL * np.abs(c['pi']).max()
+    check_elbo(classic['Li'][0], c['Li'])
+    assert np.abs(classic['gamma'] - ahead['gamma']).max() <= 2e-5
+    check_elbo(classic['Li'][0], ahead['Li'][0])
 
 
 @pytest.mark.parametrize('S', [3, 4, 8, 10, 16, 31, 32, 64])
