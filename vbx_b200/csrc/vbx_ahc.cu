@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kLinkThreads) ahc_linkage_kernel(const int64_t
             }
         }
         __syncthreads();
-        if (s_best.i == INT_MAX) {
+        if (s_best.i == INT_MAX || !(s_best.d < DBL_MAX)) {
             // no finite distance left (NaN x-vectors): there is nothing to merge by; mark the rest of the linkage and stop
             for (int k = step * 4 + tid; k < (T - 1) * 4; k += kLinkThreads) Z[k] = nan("");
             return;                                               // block-uniform: s_best lives in shared memory
