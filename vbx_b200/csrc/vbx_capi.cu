@@ -22,6 +22,9 @@ struct vbx_handle_s {
     int opt_projection = 0;
     int opt_timing = 0;
     int opt_gemm = 0;  // 0 = mma.sync 3xTF32, 1 = FFMA
+    int opt_exact_stop = 1;      // 1 = finish recordings in float64 once the ELBO step nears epsilon (vbx_exact64.cu)
+    int opt_noise_c = 2;         // float32 noise bound of an ELBO difference = noise_c * 2^-24 * |ELBO|
+    int opt_guard_mult = 16;     // a recording switches when its ELBO step < epsilon + guard_mult * noise bound
     int64_t launches = 0;
     std::vector<int64_t> offsets_host;  // kept for the AHC workspace layout
     std::vector<int64_t> ahc_d_off;
@@ -92,6 +95,21 @@ size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
         w.occp = c.take<float>(LC * S);
         w.entp = c.take<float>(LC * S);
     }
+    if (pl.exact) {
+        w.active64 = c.take<int32_t>(B);
+        w.fresh = c.take<int32_t>(B);
+        w.gamma_snap = c.take<float>(2 * N * S);
+        w.pi_snap = c.take<float>(2 * B * S);
+        w.p64 = c.take<double>(N * S);
+        w.rowmax64 = c.take<double>(N);
+        w.rsig64 = c.take<double>(N);
+        w.partial64 = c.take<double>((size_t)pl.n_mtiles * S * R);
+        w.occp64 = c.take<double>((size_t)pl.n_mtiles * S);
+        w.alpha64 = c.take<double>(B * S * R);
+        w.bias64 = c.take<double>(B * S);
+        w.reg64 = c.take<double>(B);
+        w.pi64 = c.take<double>(B * S);
+    }
     if (ws) *ws = w;
     return c.off + 256;
 }
@@ -149,6 +167,20 @@ int vbx_set_option(vbx_handle_t h, const char *name, int32_t value) {
     if (!strcmp(name, "gemm")) {
         if (value != 0 && value != 1) return fail(h, VBX_ERR_ARG, "gemm must be 0 (mma 3xTF32) or 1 (FFMA)");
         h->opt_gemm = value;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "exact_stop")) {   // takes effect at the next vbx_plan (workspace layout)
+        h->opt_exact_stop = value ? 1 : 0;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "stop_noise_c")) {
+        if (value < 1) return fail(h, VBX_ERR_ARG, "stop_noise_c must be >= 1");
+        h->opt_noise_c = value;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "stop_guard_mult")) {
+        if (value < 2) return fail(h, VBX_ERR_ARG, "stop_guard_mult must be >= 2");
+        h->opt_guard_mult = value;
         return VBX_OK;
     }
     if (!strcmp(name, "timing")) {
@@ -264,6 +296,7 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
     pl.n_rec = n_rec;
     pl.R = R;
     pl.S = S;
+    pl.exact = h->opt_exact_stop;
     pl.n_frames = n_rec ? offsets_host[n_rec] : 0;
     pl.n_ltiles = (int32_t)lrec.size();
     pl.n_mtiles = (int32_t)mrec.size();
@@ -438,35 +471,57 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
     rp.Fb = (float)Fb;
     rp.FaFb = (float)(Fa / Fb);
     rp.loopP = (float)loop_prob;
+    rp.dloopP = loop_prob;
     rp.max_iters = max_iters;
+    // epsilon = -inf (fixed iteration count) and NaN never stop: nothing to decide, everything stays float32
+    rp.hybrid = (pl.exact && epsilon > -1e300 && epsilon < 1e300 && max_iters > 1) ? 1 : 0;
+    rp.warm = warm_start ? 1 : 0;
+    rp.noise_c = (double)h->opt_noise_c;
+    rp.guard_mult = (double)h->opt_guard_mult;
 
     {
         Timed t(h, st, VBX_K_RUN_INIT);
         rc = counted(h, vbx::launch_run_init(pl, h->ws, gamma_io, n_states, Li_out, n_iters_out, flags_out, max_iters, st), "run_init");
     }
     if (rc) return rc;
-    for (int it = 0; it < max_iters; ++it) {
+    // With the float64 finishing phase a recording that switched lags one round behind (it redoes two iterations):
+    // one extra round, in which only the float64 kernels run.
+    const int rounds = max_iters + (rp.hybrid ? 1 : 0);
+    for (int it = 0; it < rounds; ++it) {
         const bool given = it == 0 && warm_start;
-        if (!given) {
-            Timed t(h, st, VBX_K_MSTEP);
-            rc = counted(h, h->opt_gemm ? vbx::launch_mstep_partial(pl, h->ws, rho, gamma_io, st) : vbx::launch_mstep_mma(pl, h->ws, rho, gamma_io, st), "mstep_partial");
+        if (it < max_iters) {
+            if (rp.hybrid) {   // state entering this iteration, for recordings that switch to float64 later
+                Timed t(h, st, VBX_K_EXACT64);
+                rc = counted(h, vbx::launch_snapshot(pl, h->ws, gamma_io, pi_io, it, st), "snapshot");
+                if (rc) return rc;
+            }
+            if (!given) {
+                Timed t(h, st, VBX_K_MSTEP);
+                rc = counted(h, h->opt_gemm ? vbx::launch_mstep_partial(pl, h->ws, rho, gamma_io, st) : vbx::launch_mstep_mma(pl, h->ws, rho, gamma_io, st), "mstep_partial");
+            }
+            if (rc) return rc;
+            {
+                Timed t(h, st, VBX_K_SPEAKER_MODEL);
+                rc = counted(h, vbx::launch_speaker_model(pl, h->ws, rp, Phi, n_states, alpha_io, invL_io, given, st), "speaker_model");
+            }
+            if (rc) return rc;
+            {
+                Timed t(h, st, VBX_K_LOGLIK);
+                rc = counted(h, h->opt_gemm ? vbx::launch_loglik(pl, h->ws, rho, st) : vbx::launch_loglik_mma(pl, h->ws, rho, st), "loglik");
+            }
+            if (rc) return rc;
+            {
+                Timed t(h, st, VBX_K_FWDBWD);
+                rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, h->opt_fb_classic, st), "forward_backward");
+            }
+            if (rc) return rc;
         }
-        if (rc) return rc;
-        {
-            Timed t(h, st, VBX_K_SPEAKER_MODEL);
-            rc = counted(h, vbx::launch_speaker_model(pl, h->ws, rp, Phi, n_states, alpha_io, invL_io, given, st), "speaker_model");
+        if (rp.hybrid && it > 0) {   // one float64 iteration for the recordings in the finishing phase (none at it == 0)
+            Timed t(h, st, VBX_K_EXACT64);
+            rc = counted(h, vbx::launch_exact64_round(pl, h->ws, rp, rho, Phi, gamma_io, pi_io, n_states, alpha_io, invL_io, Li_out,
+                                                      n_iters_out, flags_out, st), "exact64");
+            if (rc) return rc;
         }
-        if (rc) return rc;
-        {
-            Timed t(h, st, VBX_K_LOGLIK);
-            rc = counted(h, h->opt_gemm ? vbx::launch_loglik(pl, h->ws, rho, st) : vbx::launch_loglik_mma(pl, h->ws, rho, st), "loglik");
-        }
-        if (rc) return rc;
-        {
-            Timed t(h, st, VBX_K_FWDBWD);
-            rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, h->opt_fb_classic, st), "forward_backward");
-        }
-        if (rc) return rc;
     }
     return VBX_OK;
 }

@@ -20,6 +20,7 @@ constexpr int kMaxS = 64;
 // Device-resident description of a planned batch (arrays owned by the handle).
 struct Plan {
     int32_t n_rec = 0, R = 0, S = 0;
+    int32_t exact = 0;                  // 1 = the workspace holds the buffers of the float64 finishing phase
     int64_t n_frames = 0;
     int32_t n_ltiles = 0, n_mtiles = 0;
     int64_t max_T = 0;
@@ -54,7 +55,22 @@ struct Workspace {
     double *gsum = nullptr;    // [n_rec]      sum_t G_t
     double *gpart = nullptr;   // [n_mtiles]
     double *prev_elbo = nullptr; // [n_rec]
-    int32_t *active = nullptr; // [n_rec]
+    int32_t *active = nullptr; // [n_rec]  1 = the recording is iterating in the float32 kernels
+    // float64 finishing phase (vbx_exact64.cu); null when the plan was made with option "exact_stop" = 0
+    int32_t *active64 = nullptr; // [n_rec] 1 = iterating in the float64 kernels
+    int32_t *fresh = nullptr;    // [n_rec] 1/2 = the next float64 iteration is the recording's first (restore the snapshot);
+                                 //         1: its stop test is already decided (no stop), 2: test against the float32 ELBO
+    float *gamma_snap = nullptr; // [2][N,S]   gamma at the start of float32 iteration i lives in slot i % 2
+    float *pi_snap = nullptr;    // [2][n_rec,S]
+    double *p64 = nullptr;       // [N,S]
+    double *rowmax64 = nullptr;  // [N]
+    double *rsig64 = nullptr;    // [N]
+    double *partial64 = nullptr; // [n_mtiles,S,R]
+    double *occp64 = nullptr;    // [n_mtiles,S]
+    double *alpha64 = nullptr;   // [n_rec,S,R]
+    double *bias64 = nullptr;    // [n_rec,S]
+    double *reg64 = nullptr;     // [n_rec]
+    double *pi64 = nullptr;      // [n_rec,S]
     float *scratch = nullptr;  // [2*kMaxS] write sink for warp lanes that own no recording
     // chunked scan of long recordings: per (chunk, basis) operators and per-chunk boundary vectors / partial sums
     float *fa_u = nullptr, *fa_lam = nullptr, *fa_exp = nullptr, *astart = nullptr;   // [LC,S,S], [LC,S] mantissa, [LC,S] exponent, [LC,S]
@@ -64,8 +80,12 @@ struct Workspace {
 
 struct RunParams {
     float Fa, Fb, FaFb, loopP;
-    double dFa, dFb, dFaFb, epsilon;
+    double dFa, dFb, dFaFb, dloopP, epsilon;
     int32_t max_iters;
+    // stop rule at float64 resolution (vbx_exact64.cu): a recording leaves the float32 kernels when its ELBO step is
+    // below epsilon + guard_mult * nb, nb = noise_c * 2^-24 * |ELBO| (bound on the float32 noise of an ELBO difference)
+    int32_t hybrid, warm;
+    double noise_c, guard_mult;
 };
 
 #ifdef __CUDACC__
@@ -164,6 +184,11 @@ int launch_forward_backward_long(const Plan &pl, const Workspace &ws, const RunP
 // tensor-core (mma.sync 3xTF32) versions of the two in-loop contractions (vbx_mma_kernels.cu)
 int launch_mstep_mma(const Plan &pl, const Workspace &ws, const float *rho, const float *gamma, cudaStream_t st);
 int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st);
+// float64 finishing phase of vbx_run (vbx_exact64.cu)
+int launch_snapshot(const Plan &pl, const Workspace &ws, const float *gamma, const float *pi, int iter, cudaStream_t st);
+int launch_exact64_round(const Plan &pl, const Workspace &ws, const RunParams &rp, const float *rho, const float *Phi,
+                         float *gamma, float *pi, const int32_t *n_states, float *alpha_io, float *invL_io, double *Li,
+                         int32_t *n_iters, int32_t *flags, cudaStream_t st);
 // float64 "exact" path (vbx_f64.cu)
 size_t f64_workspace_bytes(const Plan &pl);
 int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const double *Phi, double *gamma, double *pi,

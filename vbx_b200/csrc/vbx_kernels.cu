@@ -224,6 +224,10 @@ __global__ void __launch_bounds__(128) run_init_kernel(Plan pl, Workspace ws, co
     const bool ok = T > 0 && ns > 0;
     if (tid == 0) {
         ws.active[rec] = ok ? 1 : 0;
+        if (ws.active64) {
+            ws.active64[rec] = 0;
+            ws.fresh[rec] = 0;
+        }
         ws.prev_elbo[rec] = 0.0;
         n_iters[rec] = 0;
         flags[rec] = 0;
@@ -1243,12 +1247,35 @@ __global__ void __launch_bounds__(128) elbo_kernel(Plan pl, Workspace ws, RunPar
         double reg = 0.0;                         // eq. (25) regulariser: per-speaker parts in speaker order
         for (int s = 0; s < pl.S; ++s) reg += ws.regp[(int64_t)rec * pl.S + s];
         const double elbo = (part[0] + part[1]) + (part[2] + part[3]) + rp.dFa * ws.gsum[rec] + 0.5 * rp.dFb * reg;
+        const double d = elbo - ws.prev_elbo[rec];
+        if (rp.hybrid && iter > 0 && isfinite(elbo)) {
+            // float32 resolves an ELBO difference to about nb; decide here only what is decided safely
+            const double nb = rp.noise_c * 5.9604644775390625e-8 * fabs(elbo);
+            const bool go_on = d >= rp.epsilon + rp.guard_mult * nb;     // far above epsilon: keep iterating in float32
+            const bool stop = d < rp.epsilon - nb;                        // clearly below epsilon: the reference stops too
+            if (!go_on && !stop) {
+                // Hand the recording to the float64 kernels (vbx_exact64.cu).  This iteration AND the previous one are
+                // discarded and redone there from the snapshot that entered iteration iter-1, so that the test of
+                // iteration iter compares two float64 ELBO values; iteration iter-1 itself was seen safely above
+                // epsilon one round ago (fresh = 1: no test).  Only a warm-started iteration 0 cannot be redone (the
+                // given model is float32): then iteration 1 alone is redone and tested against the float32 ELBO of
+                // iteration 0 if it is within float32 noise of epsilon (fresh = 2).
+                ws.active[rec] = 0;
+                ws.active64[rec] = 1;
+                if (iter == 1 && rp.warm) {
+                    ws.fresh[rec] = d >= rp.epsilon + nb ? 1 : 2;
+                } else {
+                    ws.fresh[rec] = 1;
+                    n_iters[rec] = iter - 1;
+                }
+                return;
+            }
+        }
         Li[(int64_t)rec * rp.max_iters + iter] = elbo;
         n_iters[rec] = iter + 1;
         int fl = flags[rec];
         if (!isfinite(elbo)) fl |= 1;
         if (iter > 0) {
-            const double d = elbo - ws.prev_elbo[rec];
             if (d < rp.epsilon) {  // VBx/VBx.py:122: stop AFTER this iteration's update
                 ws.active[rec] = 0;
                 if (iter + 1 < rp.max_iters) fl |= 4;
