@@ -2,21 +2,22 @@
 """Benchmark of the VB-HMM EM hot path (BASELINE.json metric: x-vectors/s through 10 EM iterations).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one JSON line on rank 0)
-    python bench.py --impl reference ...                     # the reference algorithm on the host cores
+    python bench.py --impl reference ...                     # the reference's CPU implementation on the host cores
 
-A step = one pass of the hot path over one synthetic batch: rho = X.V (projection) followed by 10 EM
-iterations (epsilon = -inf, the reference then never breaks, VBx/VBx.py:122).  `value` is measured with
-X / gamma0 resident in HBM; `e2e` goes through the host-buffer API (pinned host X and gamma0 copied in,
-gamma/pi/Li copied out, inside the timed region).  Multi-GPU: recordings are independent, every rank owns
-its own batch (weak scaling) and one NCCL all-reduce combines the per-iteration ELBO sums.
+A step = one pass of the hot path over one synthetic batch: rho = X.V (projection) followed by the workload's EM
+iterations (epsilon = -inf: the reference then never breaks, VBx/VBx.py:122).  `value` is measured with X / gamma0
+resident in HBM; `e2e` goes through the host-buffer API (pinned host X and gamma0 copied in, gamma/pi/Li copied out,
+inside the timed region).  Multi-GPU: recordings are independent; the headline workload gives every rank its own
+batch (weak scaling), `--workload c4` shards ONE fixed batch of 192 long recordings over the ranks (strong scaling);
+either way the only collective is one NCCL all-reduce of the ELBO trace, issued inside the library (vbx_elbo_trace).
+`--workload c1` times the reference's own call (VBx/vbhmm.py:154-158 on ES2005a) through the drop-in VBx().
 """
 import os
 os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")   # before numpy: the CPU baseline runs one process per core
 os.environ.setdefault("OMP_NUM_THREADS", "1")
 import argparse
+import contextlib
 import json
-import math
-import os
 import subprocess
 import sys
 import threading
@@ -31,19 +32,23 @@ if ROOT not in sys.path:
 METRIC = 'x-vectors/sec through 10 VB-HMM EM iters'
 UNIT = 'x-vectors/s'
 
-# name -> (B, T spec, S, iters, Fa, Fb, loopP)    SURVEY.md 8(d) / BASELINE.json configs
+# SURVEY.md 8(d) / BASELINE.json configs.  B = recordings per GPU, except for strong-scaling workloads (B = the whole job)
 WORKLOADS = {
     # north_star headline: 4096 recordings x T=1000, D=256 / R=128 / S=16, 10 iterations, one GPU
     'headline': dict(B=4096, T=1000, S=16, iters=10, Fa=0.3, Fb=17.0, loopP=0.99),
+    'c1': dict(B=1, T=1025, S=31, iters=40, Fa=0.3, Fb=17.0, loopP=0.99, dropin=True),    # ES2005a, the reference's own call
     'c2': dict(B=256, T=1000, S=16, iters=10, Fa=0.3, Fb=17.0, loopP=0.99),
     'c3': dict(B=4096, T=(200, 3000), S=16, iters=20, Fa=0.3, Fb=17.0, loopP=0.99),
-    'c4': dict(B=24, T=12000, S=30, iters=40, Fa=0.2, Fb=6.0, loopP=0.35),      # per GPU share of 192 recordings
+    # DIHARD-II-shaped: ONE batch of 192 long recordings sharded over the GPUs of the box (strong scaling)
+    'c4': dict(B=192, T=12000, S=30, iters=40, Fa=0.2, Fb=6.0, loopP=0.35, strong=True),
+    'c4share': dict(B=24, T=12000, S=30, iters=40, Fa=0.2, Fb=6.0, loopP=0.35),     # one GPU's share of c4 at 8 GPUs
     'c5s4': dict(B=1024, T=2000, S=4, iters=10, Fa=0.3, Fb=17.0, loopP=0.99),
     'c5s8': dict(B=1024, T=2000, S=8, iters=10, Fa=0.3, Fb=17.0, loopP=0.99),
     'c5s16': dict(B=1024, T=2000, S=16, iters=10, Fa=0.3, Fb=17.0, loopP=0.99),
     'c5s32': dict(B=1024, T=2000, S=32, iters=10, Fa=0.3, Fb=17.0, loopP=0.99),
     'c5s64': dict(B=1024, T=2000, S=64, iters=10, Fa=0.3, Fb=17.0, loopP=0.99),
     'tiny': dict(B=32, T=300, S=16, iters=10, Fa=0.3, Fb=17.0, loopP=0.99),
+    'tinystrong': dict(B=12, T=(300, 5000), S=6, iters=6, Fa=0.3, Fb=17.0, loopP=0.99, strong=True),
 }
 D_RAW, R_DIM = 256, 128
 
@@ -101,6 +106,16 @@ def make_device_batch(lengths, S, seed, device):
     return dict(X=X.contiguous(), V=V, V0=V0, Phi=Phi, gamma0=gamma0.contiguous())
 
 
+def make_device_shard(all_lengths, indices, S, seed, device):
+    """Strong scaling: recording i of the job is generated from seed + i whichever rank owns it."""
+    import torch
+    parts = [make_device_batch(all_lengths[i:i + 1], S, seed + 7919 * int(i), device) for i in indices]
+    out = dict(parts[0])
+    out['X'] = torch.cat([p['X'] for p in parts]).contiguous()
+    out['gamma0'] = torch.cat([p['gamma0'] for p in parts]).contiguous()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks sampling during the timed region (B200_PROFILING.md "clocks line")
 # ------------------------------------------------------------------------------------------------
@@ -152,44 +167,119 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference algorithm, one recording per task on all host cores
-# (the reference's own one-process-per-recording model, AMI_run.sh:53-58)
+# NUMA: the host thread that feeds a GPU, and the pinned buffers it allocates, belong on the GPU's own NUMA node
 # ------------------------------------------------------------------------------------------------
+def gpu_numa_cpus(index):
+    """(node, cpu list) of the NUMA node GPU `index` hangs off, or None."""
+    try:
+        bus = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith('00000000:'):
+            bus = bus[4:]
+        node = int(open(f'/sys/bus/pci/devices/{bus}/numa_node').read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        return (node, cpus) if cpus else None
+    except Exception:
+        return None
+
+
+@contextlib.contextmanager
+def numa_affinity(index, info):
+    """Run the body (pinned allocations + the host side of the e2e pipeline) on the GPU's NUMA node."""
+    try:
+        old = os.sched_getaffinity(0)
+    except Exception:
+        old = None
+    loc = gpu_numa_cpus(index) if old is not None else None
+    if loc:
+        try:
+            os.sched_setaffinity(0, loc[1])
+            info.update(node=loc[0], cpus=len(loc[1]))
+        except Exception:
+            loc = None
+    try:
+        yield
+    finally:
+        if loc and old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except Exception:
+                pass
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm.  The UNMODIFIED reference VBx.VBx when a copy is reachable ($VBX_REF, baseline/_ref installed with pip from
+# /root/reference, /root/reference itself), else the oracle port; one recording per process on all host cores (the
+# reference's own one-process-per-recording model, AMI_run.sh:53-58).
+# ------------------------------------------------------------------------------------------------
+def reference_dir():
+    cands = []
+    if os.environ.get('VBX_REF'):
+        cands += [os.path.join(os.environ['VBX_REF'], 'VBx'), os.environ['VBX_REF']]
+    cands += [os.path.join(ROOT, 'baseline', '_ref', 'VBx'), '/root/reference/VBx']
+    for c in cands:
+        if os.path.isfile(os.path.join(c, 'VBx.py')):
+            return c
+    return None
+
+
+_REF_FN = None
+
+
+def cpu_vbx():
+    """-> (callable with the reference's VBx() signature, kind, description)."""
+    global _REF_FN
+    if _REF_FN is None:
+        d = reference_dir()
+        if d is not None:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location('vbx_reference_module', os.path.join(d, 'VBx.py'))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _REF_FN = (mod.VBx, 'reference', f'unmodified reference VBx.VBx ({d}/VBx.py), float64 numpy')
+        else:
+            from oracle import vbx_oracle as po
+            _REF_FN = (po.vbx_oracle, 'port', 'oracle/vbx_oracle.py: float64 numpy restatement of VBx/VBx.py (log-domain '
+                       'recursions, same per-frame Python overhead as the reference)')
+    return _REF_FN
+
+
 def _cpu_task(args):
     os.environ['OPENBLAS_NUM_THREADS'] = '1'
-    X, V0, Phi, g0, S, iters, Fa, Fb, loopP = args
-    from oracle import vbx_oracle as po
-    fea = X.astype(np.float64) @ V0.astype(np.float64)        # the caller-side projection, VBx/vbhmm.py:153
+    X, V0, Phi, g0, S, iters, Fa, Fb, loopP, eps = args
+    fn = cpu_vbx()[0]
+    fea = X.astype(np.float64) @ V0.astype(np.float64) if V0 is not None else X.astype(np.float64)   # VBx/vbhmm.py:153
     t = time.perf_counter()
-    po.vbx_oracle(fea, Phi.astype(np.float64), loopProb=loopP, Fa=Fa, Fb=Fb, pi=S, gamma=g0.astype(np.float64),
-                  maxIters=iters, epsilon=-np.inf)
+    fn(fea, Phi.astype(np.float64), loopProb=loopP, Fa=Fa, Fb=Fb, pi=S, gamma=g0.astype(np.float64), maxIters=iters, epsilon=eps)
     return time.perf_counter() - t
-
-
-def cpu_baseline(sample, w, cores=None, repeats=1):
-    """sample: list of (X [T,D], g0 [T,S]) numpy arrays + shared V0, Phi.  Returns (x-vec/s, cores, wall s)."""
-    import multiprocessing as mp
-    recs, V0, Phi = sample
-    cores = cores or os.cpu_count() or 1
-    os.environ['OPENBLAS_NUM_THREADS'] = '1'
-    tasks = [(X, V0, Phi, g0, w['S'], w['iters'], w['Fa'], w['Fb'], w['loopP']) for X, g0 in recs]
-    frames = sum(X.shape[0] for X, _ in recs)
-    ctx = mp.get_context('fork')
-    best = None
-    with ctx.Pool(min(cores, len(tasks))) as pool:
-        pool.map(_cpu_warm, range(min(cores, len(tasks))))
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            pool.map(_cpu_task, tasks, chunksize=1)
-            wall = time.perf_counter() - t0
-            best = wall if best is None else min(best, wall)
-    return frames / best, min(cores, len(tasks)), best
 
 
 def _cpu_warm(_):
     os.environ['OPENBLAS_NUM_THREADS'] = '1'
-    from oracle import vbx_oracle  # noqa: F401
+    cpu_vbx()
     return 0
+
+
+def cpu_pool_run(tasks, cores, repeats=1, warmup=0):
+    import multiprocessing as mp
+    ctx = mp.get_context('fork')
+    used = min(cores, len(tasks))
+    walls = []
+    with ctx.Pool(used) as pool:
+        pool.map(_cpu_warm, range(used))
+        for i in range(warmup + repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_task, tasks, chunksize=1)
+            if i >= warmup:
+                walls.append(time.perf_counter() - t0)
+    return walls, used
 
 
 def host_sample(w, n_rec, seed):
@@ -201,64 +291,194 @@ def host_sample(w, n_rec, seed):
     return recs, synth.projection_basis(D_RAW, R_DIM), d['Phi']
 
 
-# ------------------------------------------------------------------------------------------------
+def es2005a_call():
+    """Inputs of the reference's own VBx() call on ES2005a (VBx/vbhmm.py:150-158, run_example.sh:23-34), from the
+    reference-generated fixture tests/golden/es2005a.npz."""
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'es2005a.npz'))
+    lab = z['labels_ahc'].astype(int)
+    q = np.zeros((len(lab), lab.max() + 1))
+    q[np.arange(len(lab)), lab] = 1.0
+    q = np.exp(q * float(z['smoothing']))
+    q /= q.sum(1, keepdims=True)
+    kw = dict(loopProb=float(z['loopProb']), Fa=float(z['Fa']), Fb=float(z['Fb']), maxIters=40, epsilon=1e-6)
+    return z, z['fea'], z['Phi'], q, kw
+
+
 def dist_env():
     return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 
 
+def workload_config(w, wname, n_gpus):
+    T = w['T']
+    per = 'recordings in the job' if w.get('strong') else 'recordings/GPU'
+    cfg = {'workload': f'{wname}: B={w["B"]} {per} x T={"U[%d,%d]" % T if isinstance(T, tuple) else T} '
+                       f'x D={D_RAW} -> R={R_DIM}, S={w["S"]}, {w["iters"]} EM iterations',
+           'recordings': w['B'], 'recordings_are': 'whole job (sharded over the GPUs)' if w.get('strong') else 'per GPU',
+           'frames_per_recording': list(T) if isinstance(T, tuple) else T, 'D': D_RAW,
+           'R': R_DIM, 'S': w['S'], 'em_iterations': w['iters'], 'Fa': w['Fa'], 'Fb': w['Fb'], 'loopProb': w['loopP'],
+           'parallelism': f'recordings sharded over {n_gpus} GPU(s), one NCCL all-reduce of the ELBO trace',
+           'l2': 'inputs larger than L2 (rho alone exceeds 126 MB)' if w['B'] * (np.mean(T) if isinstance(T, tuple) else T) * R_DIM * 4 / (n_gpus if w.get('strong') else 1) > 2 * 126e6
+                 else 'L2 flushed between steps (256 MB scratch write)'}
+    if w.get('dropin'):
+        cfg['workload'] = (f'{wname}: ES2005a (T=1025 x-vectors, R=128, S=31 AHC clusters), the reference call VBx/vbhmm.py:154-158 '
+                           '(maxIters=40, epsilon=1e-6 -> 13 iterations), host numpy in / out')
+        cfg['parallelism'] = 'one recording, one GPU'
+        cfg['l2'] = 'single recording (0.5 MB): L2 resident by nature, as in the reference use'
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# --impl reference
+# ------------------------------------------------------------------------------------------------
 def run_reference(args, w, wname):
-    """--impl reference: the reference's CPU algorithm (oracle port, float64 numpy, log-domain recursions) on all
-    host cores; each step = a bounded sample of the workload."""
+    """The reference's CPU implementation of the path on all host cores; each step = a bounded sample of the workload."""
     rank, _, world = dist_env()
     if rank != 0:
         return
+    fn, kind, desc = cpu_vbx()
     cores = os.cpu_count() or 1
-    n_rec = max(8, cores)
-    sample = host_sample(w, n_rec, seed=1)
-    frames = sum(x.shape[0] for x, _ in sample[0])
-    vals, walls = [], []
-    import multiprocessing as mp
-    ctx = mp.get_context('fork')
-    tasks = [(X, sample[1], sample[2], g0, w['S'], w['iters'], w['Fa'], w['Fb'], w['loopP']) for X, g0 in sample[0]]
-    with ctx.Pool(min(cores, len(tasks))) as pool:
-        pool.map(_cpu_warm, range(min(cores, len(tasks))))
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            pool.map(_cpu_task, tasks, chunksize=1)
-            dt = time.perf_counter() - t0
-            if i >= args.warmup:
-                walls.append(dt)
+    if w.get('dropin'):
+        z, fea, Phi, q, kw = es2005a_call()
+        tasks = [(fea, None, Phi, q, q.shape[1], kw['maxIters'], kw['Fa'], kw['Fb'], kw['loopProb'], kw['epsilon'])]
+        sample = 'the recording itself (ES2005a, 13 iterations until the epsilon stop), one process'
+    else:
+        n_rec = max(8, cores)
+        recs, V0, Phi = host_sample(w, n_rec, seed=1)
+        tasks = [(X, V0, Phi, g0, w['S'], w['iters'], w['Fa'], w['Fb'], w['loopP'], -np.inf) for X, g0 in recs]
+        sample = f'{len(tasks)} recordings x {w["iters"]} iterations of the workload per step, one per process'
+    frames = sum(t[0].shape[0] for t in tasks)
+    walls, used = cpu_pool_run(tasks, cores, repeats=args.steps, warmup=args.warmup)
     ms = 1e3 * float(np.mean(walls))
     value = frames / (ms / 1e3)
-    used = min(cores, len(tasks))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(w, wname, args.gpus, note=f'bounded sample: {len(tasks)} recordings ({frames} x-vectors) per step'),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port',
-                         'sample': f'{len(tasks)} recordings x {w["iters"]} iterations of the workload per step, one per process '
-                                   f'(oracle/vbx_oracle.py: float64 numpy restatement of VBx/VBx.py, OPENBLAS_NUM_THREADS=1)'},
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if w.get('strong') else 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'real (ES2005a fixture)' if w.get('dropin') else 'synthetic',
+        'config': workload_config(w, wname, args.gpus),
+        'note': f'bounded sample: {len(tasks)} recording(s) ({frames} x-vectors) per step',
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': kind, 'sample': f'{sample}; {desc}, OPENBLAS_NUM_THREADS=1'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(w, wname, n_gpus, note=None):
-    T = w['T']
-    cfg = {'workload': f'{wname}: B={w["B"]} recordings/GPU x T={"U[%d,%d]" % T if isinstance(T, tuple) else T} '
-                       f'x D={D_RAW} -> R={R_DIM}, S={w["S"]}, {w["iters"]} EM iterations',
-           'recordings_per_gpu': w['B'], 'frames_per_recording': list(T) if isinstance(T, tuple) else T, 'D': D_RAW,
-           'R': R_DIM, 'S': w['S'], 'em_iterations': w['iters'], 'Fa': w['Fa'], 'Fb': w['Fb'], 'loopProb': w['loopP'],
-           'parallelism': f'recordings sharded over {n_gpus} GPU(s), one NCCL all-reduce of the ELBO trace',
-           'l2': 'inputs larger than L2 (rho alone exceeds 126 MB)' if w['B'] * (np.mean(T) if isinstance(T, tuple) else T) * R_DIM * 4 > 2 * 126e6
-                 else 'L2 flushed between steps (256 MB scratch write)'}
-    if note:
-        cfg['note'] = note
-    return cfg
+# ------------------------------------------------------------------------------------------------
+# --workload c1: the drop-in VBx() on the reference's own call
+# ------------------------------------------------------------------------------------------------
+def run_c1(args, w, wname):
+    import torch
+    import vbx_b200.api as api
+    from vbx_b200.batch import VbxBatch
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    z, fea, Phi, q, kw = es2005a_call()
+    T, S = q.shape
+    call = lambda: api.VBx(fea, Phi, pi=S, gamma=q, **kw)
+    default = api.PRECISION                  # what a caller of the drop-in gets without configuring anything
+    modes = {}
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_all0 = time.time()
+    for prec in ('float64', 'float32'):
+        api.set_precision(prec)
+        api.clear_plan_cache()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g, p, L = call()                      # cold: handle + plan + workspace are created inside
+        cold = time.perf_counter() - t0
+        for _ in range(max(args.warmup, 3)):
+            call()
+        ts = []
+        for _ in range(max(args.steps, 10)):
+            t0 = time.perf_counter()
+            g, p, L = call()
+            ts.append(time.perf_counter() - t0)
+        modes[prec] = dict(cold_ms=1e3 * cold, warm_ms=1e3 * float(np.median(ts)), warm_ms_min=1e3 * float(np.min(ts)), iterations=len(L),
+                           max_abs_gamma_vs_reference=float(np.abs(g - z['gamma']).max()), max_abs_pi_vs_reference=float(np.abs(p - z['pi']).max()),
+                           max_rel_elbo_vs_reference=float(np.max(np.abs(np.array([l[0] for l in L[:13]]) - z['Li'][:len(L[:13])]) / np.abs(z['Li'][:len(L[:13])]))),
+                           labels_equal=bool(np.array_equal(g.argmax(1), z['labels'])))
+    api.set_precision(default)
+    # device-resident: the same EM loop on CUDA tensors through the batch API (float32 kernels + float64 finish)
+    vb = VbxBatch([T], fea.shape[1], S, device=dev)
+    vb.set_option('gemm', 1)
+    vb.set_option('timing', 1)
+    fea_d = torch.from_numpy(fea.astype(np.float32)).to(dev)
+    phi_d = torch.from_numpy(Phi.astype(np.float32)).to(dev)
+    q_d = torch.zeros((T, vb.S), dtype=torch.float32, device=dev)
+    g_d = torch.empty_like(q_d)
+    q_d[:, :S] = torch.from_numpy(q.astype(np.float32)).to(dev)
+    p_d = torch.zeros((1, vb.S), dtype=torch.float32, device=dev)
+    evs = []
+    l0 = None
+    for i in range(3 + max(args.steps, 10)):
+        if i == 3:
+            torch.cuda.synchronize()
+            vb.timings(reset=True)
+            l0 = vb.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        vb.prepare_scale(fea_d, phi_d)
+        g_d.copy_(q_d)
+        p_d.zero_()
+        p_d[0, :S] = 1.0 / S
+        out = vb.run(g_d, p_d, Fa=kw['Fa'], Fb=kw['Fb'], loopProb=kw['loopProb'], maxIters=40, epsilon=1e-6)
+        e1.record()
+        if i >= 3:
+            evs.append((e0, e1))
+    torch.cuda.synchronize()
+    res_ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+    n_steps = len(evs)
+    launches = (vb.launches - l0) / n_steps
+    timings = vb.timings(reset=True)
+    n_it = int(out['n_iters'][0].item())
+    clocks = sampler.stop(t_all0, time.time())
+    m = modes[default]
+    kernels = {k: {'ms_per_step': v[0] / n_steps, 'launches_per_step': v[1] / n_steps} for k, v in timings.items() if v[1]}
+    # the call is launch/latency bound: a roofline fraction against HBM is reported for completeness only
+    peaks = load_peaks()
+    alg_bytes = T * (4 * R_DIM + 4 * S + 2 * 4 * R_DIM * n_it)
+    line = {
+        'metric': METRIC, 'value': T / (res_ms / 1e3), 'unit': UNIT, 'n_gpus': 1, 'steps': n_steps, 'warmup': 3,
+        'ms_per_step': res_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 kernels + f64 finishing phase',
+        'data': 'real: ES2005a x-vectors projected by the reference chain (fixture tests/golden/es2005a.npz)',
+        'config': workload_config(w, wname, 1),
+        'note': f'value = device-resident batch API (CUDA tensors in/out, {n_it} iterations until the epsilon stop); e2e = the drop-in VBx() '
+                f'with host numpy arrays in and out, precision {default!r}; both modes listed under dropin',
+        'iterations': n_it, 'reference_iterations': 13,
+        'e2e': {'value': T / (m['warm_ms'] / 1e3), 'unit': UNIT, 'ms_per_step': m['warm_ms'], 'cold_ms': m['cold_ms'],
+                'h2d_bytes_per_step': int(fea.nbytes + Phi.nbytes + q.nbytes), 'd2h_bytes_per_step': int(q.nbytes + 8 * S + 8 * 40),
+                'api': f'vbx_b200.api.VBx (the reference signature), precision {default!r}, plan cached across calls (warm) / created inside (cold)'},
+        'dropin': modes,
+        'roofline': {'bound': 'hbm', 'kernel': 'whole call (latency bound: one recording cannot fill the GPU)', 'achieved': alg_bytes / (res_ms * 1e-3) / 1e9,
+                     'peak': peaks[0], 'unit': 'GB/s', 'frac': alg_bytes / (res_ms * 1e-3) / 1e9 / peaks[0], 'traffic': None, 'peak_source': peaks[1]},
+        'kernels': kernels, 'gpu_launches': launches * n_steps, 'gpu_launches_per_step': launches, 'clocks': clocks,
+    }
+    if not args.no_cpu_baseline:
+        fn, kind, desc = cpu_vbx()
+        tasks = [(fea, None, Phi, q, S, 40, kw['Fa'], kw['Fb'], kw['loopProb'], 1e-6)]
+        walls, used = cpu_pool_run(tasks, 1, repeats=2, warmup=1)
+        line['cpu_baseline'] = {'value': T / min(walls), 'unit': UNIT, 'cores': 1, 'kind': kind, 'wall_s': min(walls),
+                                'sample': f'the same call on the same recording, one process (run_example.sh runs one); {desc}'}
+    print(json.dumps(line), flush=True)
 
 
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        if 'hbm_gbs' in peaks:
+            return float(peaks['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        pass
+    return 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -268,9 +488,11 @@ def main():
     ap.add_argument('--workload', default='headline', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--fb-spl', type=int, default=0)
     ap.add_argument('--projection', type=int, default=0)
     ap.add_argument('--fb-classic', type=int, default=0, help='1 = normalise-every-frame forward-backward sweep (A/B against the look-ahead kernel)')
+    ap.add_argument('--opt', action='append', default=[], help='name=value passed to vbx_set_option (A/B runs)')
     ap.add_argument('--front', default='project', choices=['project', 'xvectors'],
                     help="what feeds the EM loop: 'project' = rho = X.V (the headline definition, SURVEY 8d); 'xvectors' = the "
                          "real-data chain vbx_prepare_xvectors (x-vector transform + PLDA projection, two tcgen05 passes)")
@@ -280,9 +502,12 @@ def main():
     w, wname = WORKLOADS[args.workload], args.workload
     if args.impl == 'reference':
         return run_reference(args, w, wname)
+    if w.get('dropin'):
+        return run_c1(args, w, wname)
 
     import torch
     import torch.distributed as dist
+    from vbx_b200 import shard
     from vbx_b200.batch import VbxBatch
     from vbx_b200.host_pipeline import HostPipeline
 
@@ -303,10 +528,17 @@ def main():
             print(f'[rank {rank}] {msg}', file=sys.stderr, flush=True)
 
     def time_workload(w, wname, steps, warmup, with_clocks):
-        lengths = workload_lengths(w, seed=1000 + rank)
-        data = make_device_batch(lengths, w['S'], seed=17 + rank, device=device)
+        strong = bool(w.get('strong'))
+        if strong:          # one fixed job, LPT-partitioned over the ranks (vbx_b200/shard.py)
+            all_lengths = workload_lengths(w, seed=1000)
+            mine = shard.partition(all_lengths, world)[rank]
+            lengths = all_lengths[mine]
+            data = make_device_shard(all_lengths, mine, w['S'], seed=17, device=device)
+        else:               # every rank owns its own batch
+            lengths = workload_lengths(w, seed=1000 + rank)
+            data = make_device_batch(lengths, w['S'], seed=17 + rank, device=device)
         N = int(lengths.sum())
-        dbg(f'{wname}: data on device, N={N}')
+        dbg(f'{wname}: data on device, {len(lengths)} recordings, N={N}')
         vb = VbxBatch(lengths, R_DIM, w['S'], device=device)
         if args.fb_spl:
             vb.set_option('fb_states_per_lane', args.fb_spl)
@@ -314,14 +546,18 @@ def main():
             vb.set_option('projection', args.projection)
         if args.fb_classic:
             vb.set_option('fb_classic', 1)
+        for kv in args.opt:
+            k, _, v = kv.partition('=')
+            vb.set_option(k, int(v))
         vb.set_option('timing', 1)
+        in_library_collective = vb.attach_comm() if world > 1 else False
         S = vb.S
         rho = torch.empty((N, R_DIM), dtype=torch.float32, device=device)
         gamma = torch.zeros((N, S), dtype=torch.float32, device=device)
         pi = torch.empty((len(lengths), S), dtype=torch.float32, device=device)
         pi0 = torch.zeros(S, device=device)
         pi0[:w['S']] = 1.0 / w['S']
-        elbo_sum = torch.zeros(w['iters'], dtype=torch.float64, device=device)
+        trace = torch.zeros(2 * w['iters'], dtype=torch.float64, device=device)
         flush = None
         if N * R_DIM * 4 <= 2 * 126e6:
             flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -344,10 +580,7 @@ def main():
             gamma[:, :w['S']].copy_(data['gamma0'])
             pi.copy_(pi0.expand_as(pi))
             out = vb.run(gamma, pi, Fa=w['Fa'], Fb=w['Fb'], loopProb=w['loopP'], maxIters=w['iters'], epsilon=-float('inf'))
-            s = out['Li'].sum(0)
-            if world > 1:
-                dist.all_reduce(s)       # the one collective of the path: global ELBO trace
-            elbo_sum.copy_(s)
+            trace.copy_(vb.elbo_trace(out['Li']))      # the one collective of the path, inside the library (NCCL)
             return out
 
         for _ in range(warmup):
@@ -392,10 +625,37 @@ def main():
             N_total = N
         timings = vb.timings(reset=True)
         launches = (vb.launches - l0) / steps
-        assert bool(torch.isfinite(elbo_sum).all()), 'non-finite ELBO in the benchmark run'
-        res = dict(ms=ms, N=N, N_total=N_total, timings=timings, launches=launches, clocks=clocks, lengths=lengths,
-                   data=data, vb=vb, S=S, out=out, steps=steps)
-        return res
+        tr = trace.cpu().numpy()
+        assert np.all(np.isfinite(tr)), 'non-finite ELBO in the benchmark run'
+        n_all = world * w['B'] if not strong else w['B']
+        assert np.all(tr[w['iters']:] == n_all), (tr[w['iters']:], n_all)       # every recording of the job ran every iteration
+        return dict(ms=ms, N=N, N_total=N_total, timings=timings, launches=launches, clocks=clocks, lengths=lengths,
+                    data=data, vb=vb, S=S, out=out, steps=steps, strong=strong, trace=tr, gamma=gamma, pi=pi,
+                    in_library_collective=bool(in_library_collective))
+
+    def parity_sample(res, w, n_rec=3):
+        """Size-true check inside the bench: a few recordings of THIS batch against the float64 C oracle (the checker)."""
+        from oracle import c_oracle
+        lens = res['lengths']
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        pick = sorted(set([0, len(lens) // 2, len(lens) - 1]))[:n_rec]
+        V0 = res['data']['V0'].double().cpu().numpy()
+        Phi = res['data']['Phi'].double().cpu().numpy()
+        worst = dict(gamma=0.0, pi=0.0, elbo=0.0)
+        for b in pick:
+            lo, hi = int(offs[b]), int(offs[b + 1])
+            fea = res['data']['X'][lo:hi].double().cpu().numpy() @ V0
+            g0 = res['data']['gamma0'][lo:hi].double().cpu().numpy()
+            ref = c_oracle.vbx_oracle_batch(fea, Phi, np.array([0, hi - lo]), g0, np.full(w['S'], 1.0 / w['S']), w['Fa'], w['Fb'], w['loopP'],
+                                            w['iters'], -np.inf)
+            worst['gamma'] = max(worst['gamma'], float(np.abs(res['gamma'][lo:hi, :w['S']].double().cpu().numpy() - ref['gamma']).max()))
+            worst['pi'] = max(worst['pi'], float(np.abs(res['pi'][b, :w['S']].double().cpu().numpy() - ref['pi'][0]).max()))
+            worst['elbo'] = max(worst['elbo'], float(np.nanmax(np.abs(res['out']['Li'][b].cpu().numpy() - ref['Li'][0]) / np.abs(ref['Li'][0]))))
+        return {'recordings_checked': len(pick), 'frames_checked': int(sum(lens[b] for b in pick)), 'iterations': w['iters'],
+                'max_abs_gamma': worst['gamma'], 'max_abs_pi': worst['pi'], 'max_rel_elbo': worst['elbo'],
+                'bar': 'gamma, pi <= 1e-4 abs; ELBO <= 1e-4 relative (north_star)',
+                'ok': bool(worst['gamma'] <= 1e-4 and worst['pi'] <= 1e-4 and worst['elbo'] <= 1e-4),
+                'checker': 'oracle/vbx_oracle_c.c (float64) on the projected inputs of the sampled recordings, same iteration count'}
 
     res = time_workload(w, wname, args.steps, args.warmup, with_clocks=True)
     dbg(f'timed region done: {res["ms"]:.3f} ms/step')
@@ -403,13 +663,7 @@ def main():
     value = N_total / (ms / 1e3)
 
     # ---- roofline of the dominant kernel (CUDA events recorded inside the C ABI on the launching stream) ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak_gbs = float(peaks.get('hbm_gbs', 6650.0))
-    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    peak_gbs, peak_src = load_peaks()
     S = res['S']
     alg_bytes = {   # algorithmic bytes per frame per launch
         'project': 4 * D_RAW + 4 * R_DIM if args.front == 'project' else 4 * D_RAW + 3 * 4 * R_DIM,
@@ -439,40 +693,52 @@ def main():
         except Exception:
             pass
     step_bytes = N * (4 * D_RAW + 4 * R_DIM + 4 * w['S'] + 2 * 4 * R_DIM * w['iters'])   # N*(1600+1024*iters) at S=16
-    whole = {'algorithmic_bytes_per_step': step_bytes, 'achieved_gbs': step_bytes / (ms * 1e-3) / 1e9 * (N_total / N) / max(world, 1),
-             'frac_of_peak': step_bytes / (ms * 1e-3) / 1e9 / peak_gbs}
+    whole = {'algorithmic_bytes_per_step': step_bytes, 'achieved_gbs': step_bytes / (ms * 1e-3) / 1e9,
+             'frac_of_peak': step_bytes / (ms * 1e-3) / 1e9 / peak_gbs, 'per': 'GPU (this rank\'s frames over the max-over-ranks step time)'}
+
+    parity = None
+    if rank == 0 and not args.no_parity and args.front == 'project':
+        parity = parity_sample(res, w)
+        dbg(f'parity sample: {parity}')
 
     # ---- end-to-end through the host-buffer API (pinned host inputs, H2D + D2H inside the timed region) ----
     e2e = None
     if not args.no_e2e and args.front == 'project':
-        hp = HostPipeline(res['lengths'], D_RAW, R_DIM, w['S'], device=device)
-        Xh = torch.empty((N, D_RAW), dtype=torch.float32).pin_memory()
-        Gh = torch.empty((N, w['S']), dtype=torch.float32).pin_memory()
-        Xh.copy_(res['data']['X'])
-        Gh.copy_(res['data']['gamma0'])
-        torch.cuda.synchronize()
-        kw = dict(Fa=w['Fa'], Fb=w['Fb'], loopProb=w['loopP'], maxIters=w['iters'], epsilon=-float('inf'))
-        for _ in range(2):
-            hp.run(Xh, res['data']['V'], res['data']['Phi'], Gh, **kw)
-        barrier()
-        torch.cuda.synchronize()
-        n_e2e = max(3, min(args.steps, 5))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n_e2e):
-            o = hp.run(Xh, res['data']['V'], res['data']['Phi'], Gh, **kw)
-        e1.record()
-        torch.cuda.synchronize()
-        barrier()
+        numa = {}
+        with numa_affinity(local_rank, numa):       # pinned buffers + feeding thread on the GPU's NUMA node
+            hp = HostPipeline(res['lengths'], D_RAW, R_DIM, w['S'], device=device)
+            Xh = torch.empty((N, D_RAW), dtype=torch.float32).pin_memory()
+            Gh = torch.empty((N, w['S']), dtype=torch.float32).pin_memory()
+            Xh.copy_(res['data']['X'])
+            Gh.copy_(res['data']['gamma0'])
+            torch.cuda.synchronize()
+            kw = dict(Fa=w['Fa'], Fb=w['Fb'], loopProb=w['loopP'], maxIters=w['iters'], epsilon=-float('inf'))
+            for _ in range(2):
+                hp.run(Xh, res['data']['V'], res['data']['Phi'], Gh, **kw)
+            barrier()
+            torch.cuda.synchronize()
+            n_e2e = max(3, min(args.steps, 5))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n_e2e):
+                o = hp.run(Xh, res['data']['V'], res['data']['Phi'], Gh, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            barrier()
         ems = e0.elapsed_time(e1) / n_e2e
         if world > 1:
             t = torch.tensor([ems], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         # parity of the two paths on the same data (device-resident vs host-pipelined)
-        dmax = float((o['gamma'].to(device) - res['out']['gamma'][:, :w['S']]).abs().max())
-        e2e = {'value': N_total / (ems / 1e3), 'unit': UNIT, 'ms_per_step': ems, 'h2d_bytes_per_step': hp.h2d_bytes,
-               'd2h_bytes_per_step': hp.d2h_bytes, 'chunks': hp.n_chunks, 'max_abs_gamma_diff_vs_resident': dmax,
+        dmax = float((o['gamma'].to(device) - res['gamma'][:, :w['S']]).abs().max())
+        h2d, d2h = hp.h2d_bytes, hp.d2h_bytes
+        if world > 1:
+            tb = torch.tensor([h2d, d2h], dtype=torch.float64, device=device)
+            dist.all_reduce(tb)
+            h2d, d2h = int(tb[0].item()), int(tb[1].item())
+        e2e = {'value': N_total / (ems / 1e3), 'unit': UNIT, 'ms_per_step': ems, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'chunks': hp.n_chunks, 'max_abs_gamma_diff_vs_resident': dmax, 'numa': numa or None,
                'api': 'vbx_b200.host_pipeline.HostPipeline.run (pinned host X, gamma0 -> gamma, pi, Li on the host)'}
         del Xh, Gh, hp
         dbg('e2e done')
@@ -482,20 +748,22 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_rec = max(8, min(cores, 64))
-        sample = host_sample(w, n_rec, seed=1)
-        v, used, wall = cpu_baseline(sample, w, cores=cores)
-        cpu = {'value': v, 'unit': UNIT, 'cores': used, 'kind': 'port', 'wall_s': wall,
-               'sample': f'{len(sample[0])} recordings of the workload ({sum(x.shape[0] for x, _ in sample[0])} x-vectors, '
-                         f'{w["iters"]} iterations), one process per recording on {used} cores; oracle/vbx_oracle.py = float64 numpy '
-                         'restatement of VBx/VBx.py (log-domain recursions, same per-frame Python overhead as the reference)'}
+        recs, V0, Phi = host_sample(w, n_rec, seed=1)
+        tasks = [(X, V0, Phi, g0, w['S'], w['iters'], w['Fa'], w['Fb'], w['loopP'], -np.inf) for X, g0 in recs]
+        walls, used = cpu_pool_run(tasks, cores)
+        frames = sum(x.shape[0] for x, _ in recs)
+        fn, kind, desc = cpu_vbx()
+        cpu = {'value': frames / min(walls), 'unit': UNIT, 'cores': used, 'kind': kind, 'wall_s': min(walls),
+               'sample': f'{len(recs)} recordings of the workload ({frames} x-vectors, {w["iters"]} iterations), one process per recording on '
+                         f'{used} cores; {desc}'}
         try:
             from oracle import c_oracle
             t0 = time.perf_counter()
-            recs = sample[0][:8]
-            fea = np.concatenate([x.astype(np.float64) @ sample[1] for x, _ in recs])
-            g0 = np.concatenate([g for _, g in recs])
-            offs = np.concatenate([[0], np.cumsum([x.shape[0] for x, _ in recs])])
-            c_oracle.vbx_oracle_batch(fea, sample[2], offs, g0, np.full(w['S'], 1.0 / w['S']), w['Fa'], w['Fb'], w['loopP'], w['iters'], -np.inf)
+            sub = recs[:8]
+            fea = np.concatenate([x.astype(np.float64) @ V0 for x, _ in sub])
+            g0 = np.concatenate([g for _, g in sub])
+            offs = np.concatenate([[0], np.cumsum([x.shape[0] for x, _ in sub])])
+            c_oracle.vbx_oracle_batch(fea, Phi, offs, g0, np.full(w['S'], 1.0 / w['S']), w['Fa'], w['Fb'], w['loopP'], w['iters'], -np.inf)
             cpu['c_oracle_single_thread'] = {'value': fea.shape[0] / (time.perf_counter() - t0), 'unit': UNIT,
                                              'note': 'oracle/vbx_oracle_c.c (O(S) scaled recursion, float64), 1 thread, 8 recordings'}
         except Exception as ex:   # the C oracle is optional here
@@ -511,14 +779,18 @@ def main():
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if res['strong'] else 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic (seeded sticky-Markov speakers in PLDA space, SURVEY.md 8d; generated on the device)',
-            'config': workload_config(w, wname, world, note=None if args.front == 'project' else
-                                      'front end = vbx_prepare_xvectors (x-vector transform + PLDA projection) instead of rho = X.V; not the headline definition'),
+            'config': workload_config(w, wname, world),
             'target': {'north_star_x_vectors_per_s': 1e7, 'ratio': value / 1e7 / max(world, 1)},
             'roofline': roof, 'whole_step': whole, 'kernels': per_kernel, 'gpu_launches': res['launches'] * args.steps,
-            'gpu_launches_per_step': res['launches'], 'clocks': res['clocks'], 'e2e': e2e, 'cpu_baseline': cpu,
+            'gpu_launches_per_step': res['launches'], 'clocks': res['clocks'], 'e2e': e2e, 'cpu_baseline': cpu, 'parity': parity,
+            'elbo_trace': {'sum_per_iteration': [float(x) for x in res['trace'][:w['iters']]], 'recordings': int(res['trace'][w['iters']]),
+                           'collective': ('ncclAllReduce inside vbx_elbo_trace (communicator attached with vbx_attach_comm)' if res['in_library_collective']
+                                          else 'single GPU: no collective')},
         }
+        if args.front != 'project':
+            line['note'] = 'front end = vbx_prepare_xvectors (x-vector transform + PLDA projection) instead of rho = X.V; not the headline definition'
         if extra:
             line['other_workloads'] = extra
         print(json.dumps(line), flush=True)

@@ -58,7 +58,12 @@ int vbx_create(int32_t device, vbx_handle_t *out);
 int vbx_destroy(vbx_handle_t h);
 const char *vbx_last_error(vbx_handle_t h);
 
-/* Tuning knobs (ints): "fb_states_per_lane" (0 = auto, 1, 2, 4), "fb_classic" (forward-backward sweep: 0 = one-step
+/* Options (ints).  "exact_stop" (default 1; read by the next vbx_plan): 1 = the workspace also holds the buffers of the
+ * float64 finishing phase and vbx_run applies the stop rule of VBx/VBx.py:122-125 at float64 resolution (a recording
+ * leaves the float32 kernels when its ELBO step comes within a guard band of epsilon, see vbx_run); 0 = float32 only.
+ * "stop_noise_c" (default 2) / "stop_guard_mult" (default 16): the guard band = epsilon + guard_mult * nb with
+ * nb = noise_c * 2^-24 * |ELBO|, the bound used for the float32 noise of an ELBO difference.
+ * Tuning knobs: "fb_states_per_lane" (0 = auto, 1, 2, 4), "fb_classic" (forward-backward sweep: 0 = one-step
  * look-ahead recurrences, 1 = normalise-every-frame), "projection" (0 = auto, 1 = FFMA tiles,
  * 2 = tcgen05 3xTF32), "gemm" (in-loop contractions: 0 = tensor cores in split-precision 3xTF32, 1 = FFMA),
  * "timing" (0/1, see vbx_get_timings).  Unknown names return VBX_ERR_ARG. */
@@ -104,6 +109,10 @@ int vbx_prepare_xvectors(vbx_handle_t h, const float *x_raw, int32_t Dx, const f
  *   Li_out    [n_rec,max_iters] float64 ELBO trace, NaN after the last executed iteration (VBx/VBx.py:105)
  *   n_iters_out [n_rec] iterations executed (the epsilon stop of VBx/VBx.py:122-125 is per recording)
  *   flags_out [n_rec] vbx_flag bits */
+/* Stop rule: with a finite epsilon (and option "exact_stop") the test `ELBO_i - ELBO_{i-1} < epsilon` is decided on
+ * float32 ELBO values only while the step is far from epsilon; a recording whose step comes near it re-evaluates its
+ * last two iterations and all following ones in float64 (inputs: the same float32 rho / gamma), so iteration counts
+ * and results follow the float64 reference.  epsilon = -inf runs exactly max_iters float32 iterations. */
 int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io, float *pi_io,
             const int32_t *n_states, double Fa, double Fb, double loop_prob, int32_t max_iters, double epsilon,
             float *alpha_io, float *invL_io, int32_t warm_start, double *Li_out, int32_t *n_iters_out,
@@ -138,6 +147,25 @@ int vbx_run_f64(vbx_handle_t h, void *workspace, size_t workspace_bytes, const d
                 double *gamma_io, double *pi_io, const int32_t *n_states, double Fa, double Fb, double loop_prob,
                 int32_t max_iters, double epsilon, double *alpha_io, double *invL_io, int32_t warm_start,
                 double *Li_out, int32_t *n_iters_out, int32_t *flags_out, void *stream);
+
+/* The module-level forward_backward(lls, tr, ip) of the reference (VBx/VBx.py:146-175) for an arbitrary transition
+ * matrix, float64, log domain, dense S x S log-sum-exp per frame as the reference computes it (the EM loop itself never
+ * takes this route: its transition matrix is diagonal + rank one).  lls [T,S], tr [S,S] (row = from), ip [S];
+ * outputs post [T,S] (state posteriors, the reference's first return value), tll [1], lfw [T,S], lbw [T,S].
+ * All device pointers, float64; needs no plan.  1 <= S <= 1024. */
+int vbx_forward_backward(vbx_handle_t h, const double *lls, const double *tr, const double *ip, int32_t T, int32_t S,
+                         double *post_out, double *tll_out, double *lfw_out, double *lbw_out, void *stream);
+
+/* Multi-GPU: recordings are independent (the reference runs one OS process per recording,
+ * AMI_run.sh:53-58), every rank owns a shard and the only exchange is the batch-wide ELBO trace.
+ * vbx_attach_comm: hand the library an NCCL communicator the CALLER owns (an ncclComm_t, e.g. torch.distributed's; NULL
+ *   detaches).  libnccl_path may be NULL: the library resolves ncclAllReduce from the libnccl.so.2 already loaded in the
+ *   process.
+ * vbx_elbo_trace: trace_out[i] = sum over this handle's recordings of Li[rec][i], trace_out[max_iters + i] = how many
+ *   recordings ran iteration i (Li as written by vbx_run, NaN padded); with a communicator attached the 2*max_iters
+ *   doubles are then all-reduced (sum) over the ranks, on `stream`.  Li and trace_out are device pointers. */
+int vbx_attach_comm(vbx_handle_t h, void *nccl_comm, int32_t n_ranks, const char *libnccl_path);
+int vbx_elbo_trace(vbx_handle_t h, const double *Li, int32_t max_iters, double *trace_out, void *stream);
 
 /* Number of kernels launched by this handle since creation (bench.py reports it as gpu_launches). */
 int64_t vbx_launch_count(vbx_handle_t h);

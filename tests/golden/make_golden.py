@@ -22,7 +22,7 @@ REF = os.environ.get('VBX_REF', '/root/reference')
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(REF, 'VBx'))
 
-from VBx import VBx as ref_VBx, forward_backward as ref_fb          # noqa: E402  (the reference)
+from VBx import VBx as ref_VBx, forward_backward as ref_fb, DER as ref_DER          # noqa: E402  (the reference)
 import diarization_lib as ref_dl                                     # noqa: E402  (the reference)
 from vbx_b200 import formats, synth                                  # noqa: E402
 
@@ -209,8 +209,45 @@ def ahc_cases():
     np.savez_compressed(os.path.join(HERE, 'ahc_cases.npz'), **out)
 
 
+def diagnostics_cases():
+    """The optional parts of the reference module: DER() (VBx/VBx.py:129-143), the `ref=` trace columns of VBx()
+    (VBx/VBx.py:107-109) and forward_backward() (VBx/VBx.py:146-175) with a GENERAL transition matrix."""
+    out = {}
+    rng = np.random.default_rng(2024)
+    for i, (T, S, n_ref) in enumerate([(60, 4, 4), (200, 7, 5), (33, 3, 6)]):
+        q = rng.dirichlet(np.ones(S) * 0.3, size=T)
+        ref = rng.integers(0, n_ref, size=T)
+        ref[0] = n_ref - 1                        # every reference speaker id up to the maximum exists
+        out[f'der{i}/q'] = q
+        out[f'der{i}/ref'] = ref.astype(np.int32)
+        out[f'der{i}/values'] = np.array([ref_DER(q, ref), ref_DER(q, ref, xentropy=True),
+                                          ref_DER(q, ref, expected=False), ref_DER(q, ref, expected=False, xentropy=True)])
+    # VBx(ref=...) appends [ELBO, DER, cross-entropy] per iteration
+    T, R, S = 180, 128, 6
+    Phi = synth.plda_phi(R)
+    fea, z = synth.make_recording(T, R, Phi, rng, stay=0.9, n_spk=4)
+    fea = 0.12 * fea + rng.standard_normal(fea.shape)     # weakly separated speakers: DER and cross-entropy stay away from 0
+    g0 = synth.dirichlet_rows(T, S, rng)
+    g, p, L = ref_VBx(fea, Phi, loopProb=0.9, Fa=0.3, Fb=17.0, pi=S, gamma=g0.copy(), maxIters=8, epsilon=1e-3, ref=z)
+    out.update({'trace/fea': fea, 'trace/Phi': Phi, 'trace/gamma0': g0, 'trace/ref': np.asarray(z, dtype=np.int32),
+                'trace/Li': np.array(L), 'trace/gamma': g, 'trace/pi': p})
+    print('ref= trace: %d iterations, last row %s' % (len(L), L[-1]))
+    # forward_backward with dense random transition matrices
+    for i, (T, S, scale) in enumerate([(50, 5, 3.0), (120, 30, 40.0), (1, 4, 2.0), (40, 70, 10.0)]):
+        lls = rng.standard_normal((T, S)) * scale
+        tr = rng.dirichlet(np.ones(S) * 0.5, size=S)
+        ip = rng.dirichlet(np.ones(S))
+        post, tll, lfw, lbw = ref_fb(lls, tr, ip)
+        out.update({f'fbg{i}/lls': lls, f'fbg{i}/tr': tr, f'fbg{i}/ip': ip, f'fbg{i}/post': post, f'fbg{i}/tll': tll,
+                    f'fbg{i}/lfw': lfw, f'fbg{i}/lbw': lbw})
+    np.savez_compressed(os.path.join(HERE, 'diagnostics_cases.npz'), **out)
+
+
 if __name__ == '__main__':
     np.random.seed(0)
+    if sys.argv[1:] == ['diag']:
+        diagnostics_cases()
+        sys.exit(0)
     if sys.argv[1:] == ['model']:
         es2005a_model()
         sys.exit(0)
@@ -221,3 +258,4 @@ if __name__ == '__main__':
     es2005a_model()
     ahc_cases()
     synthetic_cases()
+    diagnostics_cases()

@@ -90,4 +90,5 @@ def test_reference_arm_runs_without_a_gpu():
     assert out.returncode == 0, out.stderr[-500:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['unit'] == 'x-vectors/s'
-    assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
+    assert line['cpu_baseline']['kind'] in ('port', 'reference') and line['e2e']['h2d_bytes_per_step'] == 0
+    assert 'note' not in line['config']                    # config must equal the b200 arm's for the same workload

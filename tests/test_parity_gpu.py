@@ -53,6 +53,7 @@ def run_gpu(fea, Phi, lengths, gamma0, pi0=None, n_states=None, spl=0, gemm=0, f
     S_user = gamma0.shape[1]
     ns = np.full(len(lengths), S_user, dtype=np.int32) if n_states is None else np.asarray(n_states, dtype=np.int32)
     vb = VbxBatch(lengths, fea.shape[1], ns, device=dev(), exact_stop=exact_stop)
+    vb.workspace.fill_(0xFF)       # poison (NaN in float32 and float64): nothing may be read before it is written
     if spl:
         vb.set_option('fb_states_per_lane', spl)
     vb.set_option('gemm', gemm)

@@ -25,19 +25,83 @@ def set_precision(name):
     PRECISION = name
 
 
-def _der_diagnostic(q, ref, expected=True, xentropy=False):
-    """Host-side passthrough of the optional diagnostic VBx/VBx.py:134-143 (never used by vbhmm.py)."""
+def DER(q, ref, expected=True, xentropy=False):
+    """The optional diagnostic of the reference module (VBx/VBx.py:129-143; never called by vbhmm.py): diarization error
+    rate or per-frame cross-entropy of the posteriors q [T,S] against integer reference labels ref [T], under the best
+    one-to-one mapping of reference speakers to HMM states.  expected=False scores the hard decisions argmax(q).
+    Host-side (numpy + scipy's Hungarian solver): it is a scoring aid, not part of the GPU path."""
     from scipy.optimize import linear_sum_assignment
-    from scipy.sparse import coo_matrix
+    q = np.asarray(q, dtype=np.float64)
+    ref = np.asarray(ref).astype(np.int64).reshape(-1)
+    n_frames = ref.shape[0]
+    if q.shape[0] != n_frames:
+        raise ValueError('DER: q and ref disagree on the number of frames')
     if not expected:
-        q = coo_matrix((np.ones(len(q)), (range(len(q)), q.argmax(1)))).toarray()
-    ref_mx = coo_matrix((np.ones(len(ref)), (range(len(ref)), ref)))
-    err_mx = ref_mx.T.dot(-np.log(q + np.nextafter(0, 1)) if xentropy else -q)
-    min_cost = err_mx[linear_sum_assignment(err_mx)].sum()
-    return min_cost / float(len(ref)) if xentropy else (len(ref) + min_cost) / float(len(ref))
+        hard = np.zeros_like(q)
+        hard[np.arange(n_frames), q.argmax(axis=1)] = 1.0
+        q = hard
+    frame_cost = -np.log(q + np.nextafter(0, 1)) if xentropy else -q
+    # cost[r, s] = total cost of explaining the frames of reference speaker r with state s
+    cost = np.zeros((int(ref.max()) + 1 if n_frames else 0, q.shape[1]))
+    np.add.at(cost, ref, frame_cost)
+    rows, cols = linear_sum_assignment(cost)
+    best = cost[rows, cols].sum()
+    return best / float(n_frames) if xentropy else (n_frames + best) / float(n_frames)
 
 
-DER = _der_diagnostic
+def forward_backward(lls, tr, ip):
+    """The module-level forward_backward() of the reference (VBx/VBx.py:146-175) on the GPU, for any transition matrix:
+    returns (state posteriors [T,S], total log-likelihood, log-forward [T,S], log-backward [T,S]) as float64 numpy."""
+    import ctypes
+    lls = np.ascontiguousarray(lls, dtype=np.float64)
+    tr = np.ascontiguousarray(tr, dtype=np.float64)
+    ip = np.ascontiguousarray(ip, dtype=np.float64)
+    T, S = lls.shape
+    assert tr.shape == (S, S) and ip.shape == (S,)
+    if not torch.cuda.is_available():
+        raise _lib.VbxError('forward_backward(): no CUDA device - vbx_b200 has no CPU fallback')
+    dev = torch.device('cuda', torch.cuda.current_device())
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    if lib.vbx_create(dev.index, ctypes.byref(h)) != 0:
+        raise _lib.VbxError('vbx_create failed: no usable sm_100 device')
+    try:
+        d = lambda a: torch.from_numpy(a).to(dev)
+        lls_d, tr_d, ip_d = d(lls), d(tr), d(ip)
+        post, lfw, lbw = (torch.empty((T, S), dtype=torch.float64, device=dev) for _ in range(3))
+        tll = torch.empty(1, dtype=torch.float64, device=dev)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        rc = lib.vbx_forward_backward(h, ptr(lls_d), ptr(tr_d), ptr(ip_d), T, S, ptr(post), ptr(tll), ptr(lfw), ptr(lbw),
+                                      ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if rc != 0:
+            raise _lib.VbxError(f'vbx_forward_backward failed ({rc}): {lib.vbx_last_error(h).decode()}')
+        return post.cpu().numpy(), float(tll.item()), lfw.cpu().numpy(), lbw.cpu().numpy()
+    finally:
+        lib.vbx_destroy(h)
+
+
+# Plans (handle + device plan + workspace) of the most recent call shapes: vbhmm.py calls VBx() once per recording, a
+# service calls it with recurring shapes; re-planning costs a cudaMalloc and a dozen synchronous copies per call.
+_PLAN_CACHE = {}
+_PLAN_CACHE_SIZE = 8
+
+
+def _cached_batch(T, D, S, dev, allocate):
+    key = (int(T), int(D), int(S), dev.index, bool(allocate))
+    vb = _PLAN_CACHE.pop(key, None)
+    if vb is None:
+        vb = VbxBatch([T], D, S, device=dev, allocate=allocate)
+        vb.rho = None
+    _PLAN_CACHE[key] = vb                       # most recently used last
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
+    return vb
+
+
+def clear_plan_cache():
+    """Drop the cached plans (frees their device memory)."""
+    while _PLAN_CACHE:
+        _PLAN_CACHE.popitem()[1].close()
 
 
 def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
@@ -81,7 +145,7 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
         raise _lib.VbxError('VBx(): no CUDA device - vbx_b200 has no CPU fallback')
     if PRECISION == 'float64':
         return _vbx_f64(X, Phi, loopProb, Fa, Fb, pi, gamma, maxIters, epsilon, ref, return_model, alpha, invL, dev)
-    vb = VbxBatch([T], D, S, device=dev)
+    vb = _cached_batch(T, D, S, dev, True)
     vb.set_option('gemm', 1)      # single recording: float32 FFMA contractions (closest to the float64 reference);
     Sp = vb.S                     # the batched API defaults to tensor cores in split-precision 3xTF32
     fea_d = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(dev)
@@ -127,7 +191,6 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
     res = (gamma_out, pi_out, Li)
     if return_model:
         res = res + (out['alpha'][0, :S].double().cpu().numpy(), out['invL'][0, :S].double().cpu().numpy())
-    vb.close()
     return res
 
 
@@ -135,7 +198,7 @@ def _vbx_f64(X, Phi, loopProb, Fa, Fb, pi, gamma, maxIters, epsilon, ref, return
     """Float64 evaluation through vbx_run_f64 (include/vbx_b200.h)."""
     T, D = X.shape
     S = len(pi)
-    vb = VbxBatch([T], D, S, device=dev, allocate=False)
+    vb = _cached_batch(T, D, S, dev, False)
     Sp = vb.S
     f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
     fea_d, phi_d = f64(X), f64(Phi)
@@ -175,5 +238,4 @@ def _vbx_f64(X, Phi, loopProb, Fa, Fb, pi, gamma, maxIters, epsilon, ref, return
     res = (g[:, :S].cpu().numpy(), p[0, :S].cpu().numpy(), Li)
     if return_model:
         res = res + (out['alpha'][0, :S].cpu().numpy(), out['invL'][0, :S].cpu().numpy())
-    vb.close()
     return res

@@ -6,6 +6,7 @@ equivalent of the reference's per-recording loop VBx/vbhmm.py:120-158, where eve
 VBx() (VBx/VBx.py:27).  `run()` executes VBx/VBx.py:91-125 for all of them at once.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -30,6 +31,8 @@ class VbxBatch:
             raise VbxError('vbx_b200 needs a CUDA device (B200, sm_100); there is no CPU path')
         self.lib = _lib.load()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:       # a bare 'cuda' means the CURRENT device, not device 0
+            self.device = torch.device('cuda', torch.cuda.current_device())
         lengths = np.asarray(lengths, dtype=np.int64).reshape(-1)
         self.B = int(lengths.shape[0])
         self.lengths = lengths
@@ -46,7 +49,7 @@ class VbxBatch:
         self.S = _lib.padded_states(int(ns.max()) if self.B else 1)
         self.uniform_states = bool(np.all(ns == self.S))
         self._h = ctypes.c_void_p()
-        rc = self.lib.vbx_create(self.device.index or 0, ctypes.byref(self._h))
+        rc = self.lib.vbx_create(self.device.index, ctypes.byref(self._h))
         if rc != 0:
             raise VbxError(f'vbx_create failed ({rc}): no usable sm_100 device')
         self.exact_stop = bool(exact_stop)
@@ -83,6 +86,44 @@ class VbxBatch:
             self.close()
         except Exception:
             pass
+
+    def attach_comm(self, group=None):
+        """Hand torch.distributed's NCCL communicator of `group` (default: the world) to the library, which then
+        all-reduces the ELBO trace itself (vbx_elbo_trace).  No-op outside a multi-rank NCCL job."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+            return False
+        pg = (group or dist.distributed_c10d._get_default_group())._get_backend(self.device)
+        if not hasattr(pg, '_comm_ptr'):
+            raise VbxError('this torch build does not expose the NCCL communicator (ProcessGroupNCCL._comm_ptr)')
+        try:
+            ptr = pg._comm_ptr()
+        except Exception:
+            ptr = 0
+        if not ptr:           # communicators are created lazily: force it with one collective, then ask again
+            t = torch.zeros(1, device=self.device)
+            dist.all_reduce(t, group=group)
+            torch.cuda.current_stream(self.device).synchronize()
+            ptr = pg._comm_ptr()
+        nccl_lib = None
+        try:
+            import nvidia.nccl
+            cand = os.path.join(list(nvidia.nccl.__path__)[0], 'lib', 'libnccl.so.2')
+            nccl_lib = cand.encode() if os.path.exists(cand) else None
+        except Exception:
+            pass
+        self._check(self.lib.vbx_attach_comm(self._h, ctypes.c_void_p(ptr), dist.get_world_size(group), nccl_lib))
+        return True
+
+    def elbo_trace(self, Li):
+        """Li [B,maxIters] (float64 CUDA, NaN padded, as returned by run()) -> float64 CUDA tensor [2*maxIters]:
+        per-iteration ELBO sums followed by the number of recordings that ran the iteration, summed over all ranks
+        when a communicator is attached."""
+        Li = Li.contiguous()
+        n = int(Li.shape[1])
+        out = torch.empty(2 * n, dtype=torch.float64, device=self.device)
+        self._check(self.lib.vbx_elbo_trace(self._h, _ptr(Li), n, _ptr(out), self._stream()))
+        return out
 
     def set_option(self, name, value):
         self._check(self.lib.vbx_set_option(self._h, name.encode(), int(value)))

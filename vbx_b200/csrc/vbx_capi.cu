@@ -1,4 +1,7 @@
 // C ABI of vbx_b200 (include/vbx_b200.h): handle, batch plan, workspace carving, EM-loop driver.
+#include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +29,11 @@ struct vbx_handle_s {
     int opt_noise_c = 2;         // float32 noise bound of an ELBO difference = noise_c * 2^-24 * |ELBO|
     int opt_guard_mult = 16;     // a recording switches when its ELBO step < epsilon + guard_mult * noise bound
     int64_t launches = 0;
+    // NCCL communicator owned by the caller (vbx_attach_comm); ncclAllReduce is resolved from the libnccl the process
+    // already uses, so the library has no link-time dependency on NCCL
+    void *nccl_comm = nullptr;
+    int nccl_ranks = 1;
+    int (*nccl_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     std::vector<int64_t> offsets_host;  // kept for the AHC workspace layout
     std::vector<int64_t> ahc_d_off;
     size_t ahc_need = 0;
@@ -47,6 +55,27 @@ int cuda_fail(vbx_handle_t h, cudaError_t e, const char *what) {
     return fail(h, VBX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// NVTX range around an entry point (visible in nsys / ncu --nvtx timelines; no cost without a tool attached)
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) err = cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 struct Carver {
     char *base;
@@ -82,6 +111,7 @@ size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
     w.prev_elbo = c.take<double>(B);
     w.active = c.take<int32_t>(B);
     w.scratch = c.take<float>(2 * vbx::kMaxS);
+    if (pl.R == 128) w.tc_scratch = c.take<float>(vbx::tc_scratch_floats());
     {
         const size_t LC = (size_t)pl.n_lchunks;
         w.fa_u = c.take<float>(LC * S * S);
@@ -144,7 +174,7 @@ int vbx_create(int32_t device, vbx_handle_t *out) {
 
 int vbx_destroy(vbx_handle_t h) {
     if (!h) return VBX_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     if (h->plan_mem) cudaFree(h->plan_mem);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
@@ -207,7 +237,8 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
         if (T < 0) return fail(h, VBX_ERR_ARG, "vbx_plan: offsets must be non-decreasing");
         if (T > (int64_t)1 << 30) return fail(h, VBX_ERR_ARG, "vbx_plan: recording longer than 2^30 frames");
     }
-    cudaError_t e = cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
+    cudaError_t e = guard.err;
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
 
     std::vector<int32_t> order(n_rec);
@@ -339,8 +370,6 @@ int vbx_bind_workspace(vbx_handle_t h, void *workspace, size_t bytes) {
 static int check_ready(vbx_handle_t h, const char *who) {
     if (!h) return VBX_ERR_ARG;
     if (!h->planned || !h->bound) return fail(h, VBX_ERR_STATE, std::string(who) + ": plan and bind a workspace first");
-    cudaError_t e = cudaSetDevice(h->device);
-    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
     return VBX_OK;
 }
 static int counted(vbx_handle_t h, int n, const char *what) {
@@ -371,8 +400,11 @@ struct Timed {
 };
 
 int vbx_prepare_scale(vbx_handle_t h, const float *fea, const float *Phi, float *rho_out, void *stream) {
+    Range nvtx_range("vbx_prepare_scale");
     int rc = check_ready(h, "vbx_prepare_scale");
     if (rc) return rc;
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return cuda_fail(h, guard.err, "cudaSetDevice");
     if (h->plan.n_frames && (!fea || !Phi || !rho_out)) return fail(h, VBX_ERR_ARG, "vbx_prepare_scale: null pointer");
     {
         Timed t(h, (cudaStream_t)stream, VBX_K_PREPARE);
@@ -385,8 +417,11 @@ int vbx_prepare_scale(vbx_handle_t h, const float *fea, const float *Phi, float 
 
 int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *V, const float *Phi, float *rho_out,
                         void *stream) {
+    Range nvtx_range("vbx_prepare_project");
     int rc = check_ready(h, "vbx_prepare_project");
     if (rc) return rc;
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return cuda_fail(h, guard.err, "cudaSetDevice");
     if (h->plan.n_frames && (!X || !V || !Phi || !rho_out)) return fail(h, VBX_ERR_ARG, "vbx_prepare_project: null pointer");
     if (D < 32 || (D & 31)) return fail(h, VBX_ERR_ARG, "vbx_prepare_project: D must be a multiple of 32");
     cudaStream_t st = (cudaStream_t)stream;
@@ -395,7 +430,7 @@ int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *
     if (h->opt_projection != 1) {   // auto: tcgen05 when the shape allows it (R == 128, D % 32 == 0), else FFMA tiles
         std::string why;
         // the tcgen05 epilogue also emits G_t per frame into the (not yet used) rowmax scratch array
-        int n = vbx::launch_project_tcgen05(h->plan, X, D, V, Phi, rho_out, h->ws.rowmax, st, &why);
+        int n = vbx::launch_project_tcgen05(h->plan, h->ws.tc_scratch, X, D, V, Phi, rho_out, h->ws.rowmax, st, &why);
         if (n >= 0) {
             h->launches += n;
             done = true;
@@ -421,8 +456,11 @@ int vbx_prepare_project(vbx_handle_t h, const float *X, int32_t D, const float *
 int vbx_prepare_xvectors(vbx_handle_t h, const float *x_raw, int32_t Dx, const float *mean1, const float *lda,
                          const float *mean2, const float *plda_mu, const float *plda_tr, const float *plda_psi,
                          float *x_norm_out, float *rho_out, void *stream) {
+    Range nvtx_range("vbx_prepare_xvectors");
     int rc = check_ready(h, "vbx_prepare_xvectors");
     if (rc) return rc;
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return cuda_fail(h, guard.err, "cudaSetDevice");
     if (!mean1 || !lda || !mean2 || !plda_mu || !plda_tr || !plda_psi)
         return fail(h, VBX_ERR_ARG, "vbx_prepare_xvectors: null model pointer");
     if (h->plan.n_frames && (!x_raw || !x_norm_out || !rho_out)) return fail(h, VBX_ERR_ARG, "vbx_prepare_xvectors: null pointer");
@@ -433,7 +471,7 @@ int vbx_prepare_xvectors(vbx_handle_t h, const float *x_raw, int32_t Dx, const f
     {
         Timed t(h, st, VBX_K_PROJECT);
         std::string why;
-        int n = vbx::launch_xvector_chain_tcgen05(h->plan, x_raw, Dx, mean1, lda, mean2, plda_mu, plda_tr, plda_psi,
+        int n = vbx::launch_xvector_chain_tcgen05(h->plan, h->ws.tc_scratch, x_raw, Dx, mean1, lda, mean2, plda_mu, plda_tr, plda_psi,
                                                   x_norm_out, rho_out, h->ws.rowmax, st, &why);
         if (n < 0) return fail(h, VBX_ERR_CUDA, "vbx_prepare_xvectors: " + why);
         h->launches += n;
@@ -451,8 +489,11 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
             const int32_t *n_states, double Fa, double Fb, double loop_prob, int32_t max_iters, double epsilon,
             float *alpha_io, float *invL_io, int32_t warm_start, double *Li_out, int32_t *n_iters_out,
             int32_t *flags_out, void *stream) {
+    Range nvtx_range("vbx_run");
     int rc = check_ready(h, "vbx_run");
     if (rc) return rc;
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return cuda_fail(h, guard.err, "cudaSetDevice");
     if (!h->prepared) return fail(h, VBX_ERR_STATE, "vbx_run: call vbx_prepare_scale/project first (G is part of the ELBO)");
     if (max_iters < 0) return fail(h, VBX_ERR_ARG, "vbx_run: max_iters < 0");
     if (!(Fb != 0.0)) return fail(h, VBX_ERR_ARG, "vbx_run: Fb must be non-zero");
@@ -488,6 +529,7 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
     // one extra round, in which only the float64 kernels run.
     const int rounds = max_iters + (rp.hybrid ? 1 : 0);
     for (int it = 0; it < rounds; ++it) {
+        Range nvtx_iter("vbx_em_iteration");
         const bool given = it == 0 && warm_start;
         if (it < max_iters) {
             if (rp.hybrid) {   // state entering this iteration, for recordings that switch to float64 later
@@ -531,6 +573,7 @@ int vbx_hard_labels(vbx_handle_t h, const float *gamma, const int32_t *n_states,
     if (!h) return VBX_ERR_ARG;
     if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_hard_labels: call vbx_plan first");
     if (h->plan.n_frames && (!gamma || !first_out)) return fail(h, VBX_ERR_ARG, "vbx_hard_labels: null pointer");
+    DeviceGuard guard(h->device);
     return counted(h, vbx::launch_hard_labels(h->plan, gamma, n_states, first_out, second_out, (cudaStream_t)stream), "hard_labels");
 }
 
@@ -544,12 +587,14 @@ int vbx_ahc_workspace_bytes(vbx_handle_t h, size_t *bytes_out) {
 int vbx_ahc(vbx_handle_t h, const void *x, int32_t x_is_f64, int32_t dim, void *workspace, size_t workspace_bytes,
             double *Z_out, double *thr_out, void *stream) {
     if (!h) return VBX_ERR_ARG;
+    Range nvtx_range("vbx_ahc");
     if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_ahc: call vbx_plan first");
     if (dim < 1) return fail(h, VBX_ERR_ARG, "vbx_ahc: dim < 1");
     if (h->plan.n_rec == 0) return VBX_OK;
     if (!workspace || !thr_out || (h->plan.n_frames && (!x || !Z_out))) return fail(h, VBX_ERR_ARG, "vbx_ahc: null pointer");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(h, VBX_ERR_ARG, "vbx_ahc: workspace must be 256-byte aligned");
     if (workspace_bytes < h->ahc_need) return fail(h, VBX_ERR_ARG, "vbx_ahc: workspace smaller than vbx_ahc_workspace_bytes()");
+    DeviceGuard guard(h->device);
     std::string why;
     int n = vbx::launch_ahc(h->plan, h->ahc_d_off, x, x_is_f64, dim, workspace, workspace_bytes, Z_out, thr_out,
                             (cudaStream_t)stream, &why);
@@ -570,9 +615,10 @@ int vbx_run_f64(vbx_handle_t h, void *workspace, size_t workspace_bytes, const d
                 int32_t max_iters, double epsilon, double *alpha_io, double *invL_io, int32_t warm_start,
                 double *Li_out, int32_t *n_iters_out, int32_t *flags_out, void *stream) {
     if (!h) return VBX_ERR_ARG;
+    Range nvtx_range("vbx_run_f64");
     if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_run_f64: call vbx_plan first");
-    cudaError_t e = cudaSetDevice(h->device);
-    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return cuda_fail(h, guard.err, "cudaSetDevice");
     const vbx::Plan &pl = h->plan;
     if (pl.n_rec == 0) return VBX_OK;
     if (!workspace || workspace_bytes < vbx::f64_workspace_bytes(pl)) return fail(h, VBX_ERR_STATE, "vbx_run_f64: workspace too small");
@@ -585,11 +631,63 @@ int vbx_run_f64(vbx_handle_t h, void *workspace, size_t workspace_bytes, const d
                    "run_f64");
 }
 
+int vbx_forward_backward(vbx_handle_t h, const double *lls, const double *tr, const double *ip, int32_t T, int32_t S,
+                         double *post_out, double *tll_out, double *lfw_out, double *lbw_out, void *stream) {
+    if (!h) return VBX_ERR_ARG;
+    if (T < 1 || S < 1 || S > 1024) return fail(h, VBX_ERR_ARG, "vbx_forward_backward: need T >= 1 and 1 <= S <= 1024");
+    if (!lls || !tr || !ip || !post_out || !tll_out || !lfw_out || !lbw_out) return fail(h, VBX_ERR_ARG, "vbx_forward_backward: null pointer");
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return cuda_fail(h, guard.err, "cudaSetDevice");
+    return counted(h, vbx::launch_fb_dense(lls, tr, ip, T, S, post_out, tll_out, lfw_out, lbw_out, (cudaStream_t)stream), "fb_dense");
+}
+
+int vbx_attach_comm(vbx_handle_t h, void *nccl_comm, int32_t n_ranks, const char *libnccl_path) {
+    if (!h) return VBX_ERR_ARG;
+    if (!nccl_comm) {   // detach
+        h->nccl_comm = nullptr;
+        h->nccl_ranks = 1;
+        return VBX_OK;
+    }
+    if (n_ranks < 1) return fail(h, VBX_ERR_ARG, "vbx_attach_comm: n_ranks < 1");
+    if (!h->nccl_allreduce) {
+        // the NCCL this process already talks through (torch's): find it without loading a second copy
+        void *lib = nullptr;
+        if (libnccl_path && *libnccl_path) lib = dlopen(libnccl_path, RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib && libnccl_path && *libnccl_path) lib = dlopen(libnccl_path, RTLD_NOW);
+        if (!lib) return fail(h, VBX_ERR_STATE, "vbx_attach_comm: libnccl.so.2 is not loaded in this process and no usable path was given");
+        void *sym = dlsym(lib, "ncclAllReduce");
+        if (!sym) return fail(h, VBX_ERR_STATE, "vbx_attach_comm: ncclAllReduce not found");
+        h->nccl_allreduce = reinterpret_cast<int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t)>(sym);
+    }
+    h->nccl_comm = nccl_comm;
+    h->nccl_ranks = n_ranks;
+    return VBX_OK;
+}
+
+int vbx_elbo_trace(vbx_handle_t h, const double *Li, int32_t max_iters, double *trace_out, void *stream) {
+    Range nvtx_range("vbx_elbo_trace");
+    if (!h) return VBX_ERR_ARG;
+    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_elbo_trace: call vbx_plan first");
+    if (max_iters < 1 || !trace_out || (h->plan.n_rec && !Li)) return fail(h, VBX_ERR_ARG, "vbx_elbo_trace: bad argument");
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return cuda_fail(h, guard.err, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = counted(h, vbx::launch_elbo_trace(h->plan, Li, max_iters, trace_out, st), "elbo_trace");
+    if (rc) return rc;
+    if (h->nccl_comm && h->nccl_ranks > 1) {
+        // the one collective of the path: per-iteration ELBO sums and active counts over all GPUs
+        const int nrc = h->nccl_allreduce(trace_out, trace_out, (size_t)2 * max_iters, /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->nccl_comm, st);
+        if (nrc != 0) return fail(h, VBX_ERR_CUDA, "vbx_elbo_trace: ncclAllReduce failed with code " + std::to_string(nrc));
+    }
+    return VBX_OK;
+}
+
 int64_t vbx_launch_count(vbx_handle_t h) { return h ? h->launches : -1; }
 
 int vbx_get_timings(vbx_handle_t h, double *ms_out, int64_t *count_out, int32_t reset) {
     if (!h) return VBX_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
         cudaError_t e = cudaEventSynchronize(h->ev_pool[i + 1]);
         if (e != cudaSuccess) return cuda_fail(h, e, "cudaEventSynchronize");

@@ -16,6 +16,7 @@ constexpr int kLongT = 4096;   // recordings at least this long take the chunked
 constexpr int kChunk = 256;    // frames per chunk of that scan
 constexpr int kMaxR = 128;
 constexpr int kMaxS = 64;
+constexpr int kTcMaxD = 2048;  // largest raw dimension of the tcgen05 front end (bounds its scratch in the workspace)
 
 // Device-resident description of a planned batch (arrays owned by the handle).
 struct Plan {
@@ -72,6 +73,7 @@ struct Workspace {
     double *reg64 = nullptr;     // [n_rec]
     double *pi64 = nullptr;      // [n_rec,S]
     float *scratch = nullptr;  // [2*kMaxS] write sink for warp lanes that own no recording
+    float *tc_scratch = nullptr; // operand images of the tcgen05 front end (vbx_project_tc.cu); null unless R == 128
     // chunked scan of long recordings: per (chunk, basis) operators and per-chunk boundary vectors / partial sums
     float *fa_u = nullptr, *fa_lam = nullptr, *fa_exp = nullptr, *astart = nullptr;   // [LC,S,S], [LC,S] mantissa, [LC,S] exponent, [LC,S]
     float *bb_v = nullptr, *bb_mu = nullptr, *bb_exp = nullptr, *beta = nullptr;      // same shapes, backward sweep
@@ -178,6 +180,7 @@ int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStr
 int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
                             int spl, int classic, cudaStream_t st);
+int launch_elbo_trace(const Plan &pl, const double *Li, int max_iters, double *out, cudaStream_t st);
 // chunked-scan forward-backward for long recordings (vbx_long_kernels.cu)
 int launch_forward_backward_long(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                                  const int32_t *n_states, cudaStream_t st);
@@ -197,14 +200,18 @@ int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const dou
                    cudaStream_t st);
 int launch_hard_labels(const Plan &pl, const float *gamma, const int32_t *n_states, int32_t *first, int32_t *second,
                        cudaStream_t st);
+// reference-module forward_backward() for a general transition matrix (vbx_fb_dense.cu)
+int launch_fb_dense(const double *lls, const double *tr, const double *ip, int T, int S, double *post, double *tll,
+                    double *lfw, double *lbw, cudaStream_t st);
 // AHC initialisation (vbx_ahc.cu)
 size_t ahc_workspace_bytes(const int64_t *offsets_host, int n_rec, std::vector<int64_t> *d_off_host);
 int launch_ahc(const Plan &pl, const std::vector<int64_t> &d_off, const void *x, int x_is_f64, int dim, void *workspace,
                size_t workspace_bytes, double *Z_out, double *thr_out, cudaStream_t st, std::string *err);
 // tcgen05 projection (vbx_project_tc.cu)
-int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, const float *Phi, float *rho,
+size_t tc_scratch_floats();
+int launch_project_tcgen05(const Plan &pl, float *tc_scratch, const float *X, int D, const float *V, const float *Phi, float *rho,
                            float *gframe, cudaStream_t st, std::string *err);
-int launch_xvector_chain_tcgen05(const Plan &pl, const float *x_raw, int Dx, const float *mean1, const float *lda,
+int launch_xvector_chain_tcgen05(const Plan &pl, float *tc_scratch, const float *x_raw, int Dx, const float *mean1, const float *lda,
                                  const float *mean2, const float *plda_mu, const float *plda_tr, const float *psi,
                                  float *x_norm, float *rho, float *gframe, cudaStream_t st, std::string *err);
 int launch_gsum_from_frames(const Plan &pl, const Workspace &ws, const float *gframe, cudaStream_t st);

@@ -1287,6 +1287,42 @@ __global__ void __launch_bounds__(128) elbo_kernel(Plan pl, Workspace ws, RunPar
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ELBO trace of the batch: out[i] = sum over recordings of Li[rec][i] (iterations a recording did not run are NaN and
+// skipped), out[max_iters + i] = number of recordings that ran iteration i.  One CTA per iteration, fixed summation
+// order (deterministic); the caller all-reduces the 2*max_iters doubles over the GPUs (vbx_elbo_trace).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) elbo_trace_kernel(int n_rec, const double *__restrict__ Li, int max_iters, double *out) {
+    const int it = blockIdx.x, tid = threadIdx.x;
+    double s = 0.0, c = 0.0;
+    for (int r = tid; r < n_rec; r += 256) {
+        const double v = Li[(int64_t)r * max_iters + it];
+        if (v == v) {
+            s += v;
+            c += 1.0;
+        }
+    }
+    __shared__ double ss[256], cs[256];
+    ss[tid] = s;
+    cs[tid] = c;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) {
+            ss[tid] += ss[tid + off];
+            cs[tid] += cs[tid + off];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out[it] = ss[0];
+        out[max_iters + it] = cs[0];
+    }
+}
+int launch_elbo_trace(const Plan &pl, const double *Li, int max_iters, double *out, cudaStream_t st) {
+    elbo_trace_kernel<<<max_iters, 256, 0, st>>>(pl.n_rec, Li, max_iters, out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
                             int spl, int classic, cudaStream_t st) {

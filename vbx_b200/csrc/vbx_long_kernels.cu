@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(32) long_fwd_combine_kernel(Plan pl, Workspace
         for (int i = 0; i < S_PAD; ++i) {
             const float wi = __shfl_sync(0xffffffffu, wgt[i >> 5], i & 31);
 #pragma unroll
-            for (int k = 0; k < SPLc; ++k) acc[k] = fmaf(wi, cur.u[k][i], acc[k]);
+            for (int k = 0; k < SPLc; ++k) acc[k] = wi != 0.f ? fmaf(wi, cur.u[k][i], acc[k]) : acc[k];   // columns of dead states are never written
         }
         float loc = 0.f;
 #pragma unroll
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(32) long_bwd_combine_kernel(Plan pl, Workspace
         for (int i = 0; i < S_PAD; ++i) {
             const float wi = __shfl_sync(0xffffffffu, wgt[i >> 5], i & 31);
 #pragma unroll
-            for (int k = 0; k < SPLc; ++k) acc[k] = fmaf(wi, cur.u[k][i], acc[k]);
+            for (int k = 0; k < SPLc; ++k) acc[k] = wi != 0.f ? fmaf(wi, cur.u[k][i], acc[k]) : acc[k];   // columns of dead states are never written
         }
 #pragma unroll
         for (int k = 0; k < SPLc; ++k) {

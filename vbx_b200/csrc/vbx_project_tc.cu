@@ -429,57 +429,35 @@ __global__ void build_plda_v_kernel(const float *__restrict__ tr, const float *_
     }
 }
 
-struct TcState {
-    float *vimg = nullptr;
-    size_t vimg_bytes = 0;
-    float *v2 = nullptr;
-    int device = -1;
-    bool configured[3] = {false, false, false};
-};
-TcState g_tc[16];
+// cudaFuncSetAttribute is per device; everything else the launches need comes from the caller's workspace
+bool g_configured[64][3] = {};
 
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes + 2 * kTileM * 4;
 
-TcState *tc_state(size_t need_img, std::string *err) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16) {
-        if (err) *err = "device index out of range";
-        return nullptr;
-    }
-    TcState &tc = g_tc[dev];
-    if (tc.vimg_bytes < need_img) {
-        if (tc.vimg) cudaFree(tc.vimg);
-        tc.vimg = nullptr;
-        if (cudaMalloc(&tc.vimg, need_img) != cudaSuccess) {
-            if (err) *err = "cudaMalloc(V images) failed";
-            tc.vimg_bytes = 0;
-            return nullptr;
-        }
-        tc.vimg_bytes = need_img;
-    }
-    tc.device = dev;
-    return &tc;
-}
-
 // one GEMM pass [N,D] x [D,128] of the given MODE; V is row-major [D,128] in device memory
 template <int MODE>
-int launch_gemm_tc(TcState &tc, int64_t N, const float *X, int D, const float *V, const float *Phi, float *out, float *gframe,
+int launch_gemm_tc(float *vimg, int64_t N, const float *X, int D, const float *V, const float *Phi, float *out, float *gframe,
                    const float *a_off, const float *e_off, cudaStream_t st, std::string *err) {
-    if (!tc.configured[MODE]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) {
+        if (err) *err = "device index out of range";
+        return -1;
+    }
+    if (!g_configured[dev][MODE]) {
         if (cudaFuncSetAttribute(project_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) !=
             cudaSuccess) {
             if (err) *err = "cudaFuncSetAttribute(smem) failed";
             return -1;
         }
-        tc.configured[MODE] = true;
+        g_configured[dev][MODE] = true;
     }
     int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, tc.device);
-    build_v_images_kernel<<<D / kKB, 256, 0, st>>>(V, D, tc.vimg);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    build_v_images_kernel<<<D / kKB, 256, 0, st>>>(V, D, vimg);
     const int64_t n_tiles = (N + kTileM - 1) / kTileM;
     const int grid = (int)std::min<int64_t>(n_tiles, sms);
-    project_tcgen05_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(X, tc.vimg, out, N, D, Phi, gframe, a_off, e_off);
+    project_tcgen05_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(X, vimg, out, N, D, Phi, gframe, a_off, e_off);
     if (cudaGetLastError() != cudaSuccess) {
         if (err) *err = "tcgen05 projection launch failed";
         return -1;
@@ -489,7 +467,11 @@ int launch_gemm_tc(TcState &tc, int64_t N, const float *X, int D, const float *V
 
 }  // namespace
 
-int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V, const float *Phi, float *rho,
+// Scratch of the tensor-core front end inside the caller's workspace: the swizzled hi/lo images of V (2 x 16 KB per
+// 32 rows of V) for D up to kTcMaxD, and the folded PLDA matrix of the x-vector chain.
+size_t tc_scratch_floats() { return (size_t)(kTcMaxD / kKB) * 2 * 4096 + 128 * 128; }
+
+int launch_project_tcgen05(const Plan &pl, float *tc_scratch, const float *X, int D, const float *V, const float *Phi, float *rho,
                            float *gframe, cudaStream_t st, std::string *err) {
     if (pl.R != 128) {
         if (err) *err = "tcgen05 projection needs R == 128";
@@ -499,16 +481,18 @@ int launch_project_tcgen05(const Plan &pl, const float *X, int D, const float *V
         if (err) *err = "tcgen05 projection needs D to be a multiple of 32";
         return -1;
     }
+    if (D > kTcMaxD || !tc_scratch) {
+        if (err) *err = "tcgen05 projection needs D <= 2048 and a plan with R == 128";
+        return -1;
+    }
     if (pl.n_frames == 0) return 0;
-    TcState *tc = tc_state((size_t)(D / kKB) * 2 * kABytes, err);
-    if (!tc) return -1;
-    return launch_gemm_tc<0>(*tc, pl.n_frames, X, D, V, Phi, rho, gframe, nullptr, nullptr, st, err);
+    return launch_gemm_tc<0>(tc_scratch, pl.n_frames, X, D, V, Phi, rho, gframe, nullptr, nullptr, st, err);
 }
 
 // The caller-side chain of VBx/vbhmm.py:125-129,153 plus the scale of VBx/VBx.py:88-89 as two tensor-core passes:
 //   x_norm = l2norm(l2norm(x_raw - mean1) . lda - mean2)             [N,128]
 //   rho    = (x_norm - plda_mu) . (plda_tr^T * sqrt(psi))            [N,128], with G_t per frame
-int launch_xvector_chain_tcgen05(const Plan &pl, const float *x_raw, int Dx, const float *mean1, const float *lda,
+int launch_xvector_chain_tcgen05(const Plan &pl, float *tc_scratch, const float *x_raw, int Dx, const float *mean1, const float *lda,
                                  const float *mean2, const float *plda_mu, const float *plda_tr, const float *psi,
                                  float *x_norm, float *rho, float *gframe, cudaStream_t st, std::string *err) {
     if (pl.R != 128) {
@@ -519,18 +503,16 @@ int launch_xvector_chain_tcgen05(const Plan &pl, const float *x_raw, int Dx, con
         if (err) *err = "the x-vector chain needs the x-vector dimension to be a multiple of 32";
         return -1;
     }
-    if (pl.n_frames == 0) return 0;
-    TcState *tc = tc_state((size_t)(std::max(Dx, 128) / kKB) * 2 * kABytes, err);
-    if (!tc) return -1;
-    if (!tc->v2 && cudaMalloc(&tc->v2, 128 * 128 * sizeof(float)) != cudaSuccess) {
-        if (err) *err = "cudaMalloc(V2) failed";
-        tc->v2 = nullptr;
+    if (Dx > kTcMaxD || !tc_scratch) {
+        if (err) *err = "the x-vector chain needs an x-vector dimension <= 2048";
         return -1;
     }
-    int n = launch_gemm_tc<1>(*tc, pl.n_frames, x_raw, Dx, lda, nullptr, x_norm, nullptr, mean1, mean2, st, err);
+    if (pl.n_frames == 0) return 0;
+    float *v2 = tc_scratch + (size_t)(kTcMaxD / kKB) * 2 * 4096;
+    int n = launch_gemm_tc<1>(tc_scratch, pl.n_frames, x_raw, Dx, lda, nullptr, x_norm, nullptr, mean1, mean2, st, err);
     if (n < 0) return -1;
-    build_plda_v_kernel<<<64, 256, 0, st>>>(plda_tr, psi, tc->v2);
-    int m = launch_gemm_tc<2>(*tc, pl.n_frames, x_norm, 128, tc->v2, psi, rho, gframe, plda_mu, nullptr, st, err);
+    build_plda_v_kernel<<<64, 256, 0, st>>>(plda_tr, psi, v2);
+    int m = launch_gemm_tc<2>(tc_scratch, pl.n_frames, x_norm, 128, v2, psi, rho, gframe, plda_mu, nullptr, st, err);
     if (m < 0) return -1;
     return n + m + 1;
 }
