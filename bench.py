@@ -282,6 +282,21 @@ def cpu_pool_run(tasks, cores, repeats=1, warmup=0):
     return walls, used
 
 
+def bounded(w, max_T=3000, max_iters=10):
+    """The CPU arm's bounded sample: the reference's cost is linear in frames and in iterations, so long recordings are
+    cut to max_T frames and long runs to max_iters iterations; throughput is scaled back to the workload's iteration
+    count (x-vectors/s through w['iters'] iterations = x-vectors/s through k iterations * k / w['iters'])."""
+    T = w['T']
+    T2 = (min(T[0], max_T), min(T[1], max_T)) if isinstance(T, tuple) else min(T, max_T)
+    it2 = min(w['iters'], max_iters)
+    ws = dict(w, T=T2, iters=it2)
+    note = ''
+    if T2 != T or it2 != w['iters']:
+        note = (f' [bounded: recordings cut to T<={max_T}, {it2} of {w["iters"]} iterations timed, throughput scaled by {it2}/{w["iters"]} '
+                'to the workload\'s iteration count]')
+    return ws, it2 / w['iters'], note
+
+
 def host_sample(w, n_rec, seed):
     """A bounded sample of the workload generated on the host with the numpy generator (same model)."""
     from vbx_b200 import synth
@@ -343,13 +358,14 @@ def run_reference(args, w, wname):
         sample = 'the recording itself (ES2005a, 13 iterations until the epsilon stop), one process'
     else:
         n_rec = max(8, cores)
-        recs, V0, Phi = host_sample(w, n_rec, seed=1)
-        tasks = [(X, V0, Phi, g0, w['S'], w['iters'], w['Fa'], w['Fb'], w['loopP'], -np.inf) for X, g0 in recs]
-        sample = f'{len(tasks)} recordings x {w["iters"]} iterations of the workload per step, one per process'
+        ws, scale, bnote = bounded(w)
+        recs, V0, Phi = host_sample(ws, n_rec, seed=1)
+        tasks = [(X, V0, Phi, g0, ws['S'], ws['iters'], ws['Fa'], ws['Fb'], ws['loopP'], -np.inf) for X, g0 in recs]
+        sample = f'{len(tasks)} recordings x {ws["iters"]} iterations of the workload per step, one per process{bnote}'
     frames = sum(t[0].shape[0] for t in tasks)
     walls, used = cpu_pool_run(tasks, cores, repeats=args.steps, warmup=args.warmup)
     ms = 1e3 * float(np.mean(walls))
-    value = frames / (ms / 1e3)
+    value = frames / (ms / 1e3) * (1.0 if w.get('dropin') else scale)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if w.get('strong') else 'weak',
@@ -748,14 +764,16 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_rec = max(8, min(cores, 64))
-        recs, V0, Phi = host_sample(w, n_rec, seed=1)
-        tasks = [(X, V0, Phi, g0, w['S'], w['iters'], w['Fa'], w['Fb'], w['loopP'], -np.inf) for X, g0 in recs]
+        ws, scale, bnote = bounded(w)
+        recs, V0, Phi = host_sample(ws, n_rec, seed=1)
+        tasks = [(X, V0, Phi, g0, ws['S'], ws['iters'], ws['Fa'], ws['Fb'], ws['loopP'], -np.inf) for X, g0 in recs]
+        dbg('cpu baseline ...')
         walls, used = cpu_pool_run(tasks, cores)
         frames = sum(x.shape[0] for x, _ in recs)
         fn, kind, desc = cpu_vbx()
-        cpu = {'value': frames / min(walls), 'unit': UNIT, 'cores': used, 'kind': kind, 'wall_s': min(walls),
-               'sample': f'{len(recs)} recordings of the workload ({frames} x-vectors, {w["iters"]} iterations), one process per recording on '
-                         f'{used} cores; {desc}'}
+        cpu = {'value': frames / min(walls) * scale, 'unit': UNIT, 'cores': used, 'kind': kind, 'wall_s': min(walls),
+               'sample': f'{len(recs)} recordings of the workload ({frames} x-vectors, {ws["iters"]} iterations), one process per recording on '
+                         f'{used} cores; {desc}{bnote}'}
         try:
             from oracle import c_oracle
             t0 = time.perf_counter()
@@ -763,8 +781,8 @@ def main():
             fea = np.concatenate([x.astype(np.float64) @ V0 for x, _ in sub])
             g0 = np.concatenate([g for _, g in sub])
             offs = np.concatenate([[0], np.cumsum([x.shape[0] for x, _ in sub])])
-            c_oracle.vbx_oracle_batch(fea, Phi, offs, g0, np.full(w['S'], 1.0 / w['S']), w['Fa'], w['Fb'], w['loopP'], w['iters'], -np.inf)
-            cpu['c_oracle_single_thread'] = {'value': fea.shape[0] / (time.perf_counter() - t0), 'unit': UNIT,
+            c_oracle.vbx_oracle_batch(fea, Phi, offs, g0, np.full(w['S'], 1.0 / w['S']), w['Fa'], w['Fb'], w['loopP'], ws['iters'], -np.inf)
+            cpu['c_oracle_single_thread'] = {'value': fea.shape[0] / (time.perf_counter() - t0) * scale, 'unit': UNIT,
                                              'note': 'oracle/vbx_oracle_c.c (O(S) scaled recursion, float64), 1 thread, 8 recordings'}
         except Exception as ex:   # the C oracle is optional here
             cpu['c_oracle_single_thread'] = {'error': str(ex)}
