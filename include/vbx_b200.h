@@ -63,6 +63,10 @@ const char *vbx_last_error(vbx_handle_t h);
  * leaves the float32 kernels when its ELBO step comes within a guard band of epsilon, see vbx_run); 0 = float32 only.
  * "stop_noise_c" (default 2) / "stop_guard_mult" (default 16): the guard band = epsilon + guard_mult * nb with
  * nb = noise_c * 2^-24 * |ELBO|, the bound used for the float32 noise of an ELBO difference.
+ * "fb_split" (read by the next vbx_plan): 0 = auto, 1 = always, 2 = never run the forward and the backward sweep of a
+ * recording concurrently on separate warps followed by a combine pass (the choice for batches too small to fill the GPU;
+ * results differ from the fused sweep by float32 rounding only, so pin it to 1 or 2 where bit-identical results for a
+ * recording alone / inside a large batch matter).
  * Tuning knobs: "fb_states_per_lane" (0 = auto, 1, 2, 4), "fb_classic" (forward-backward sweep: 0 = one-step
  * look-ahead recurrences, 1 = normalise-every-frame), "projection" (0 = auto, 1 = FFMA tiles,
  * 2 = tcgen05 3xTF32), "gemm" (in-loop contractions: 0 = tensor cores in split-precision 3xTF32, 1 = FFMA),

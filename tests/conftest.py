@@ -22,6 +22,9 @@ def pytest_collection_modifyitems(config, items):
         have_gpu = False
     have_lib = os.path.exists(os.path.join(ROOT, 'vbx_b200', 'libvbx_b200.so'))
     if have_gpu and have_lib:
+        for item in items:         # a hung kernel must cost one test, not the whole GPU session (needs pytest-timeout)
+            if 'gpu' in item.keywords and item.get_closest_marker('timeout') is None:
+                item.add_marker(pytest.mark.timeout(180))
         return
     why = 'no CUDA device' if not have_gpu else 'vbx_b200/libvbx_b200.so not built'
     skip = pytest.mark.skip(reason=f'gpu test: {why}')

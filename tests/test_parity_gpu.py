@@ -46,13 +46,15 @@ def load_cases():
 CASES = load_cases()
 
 
-def run_gpu(fea, Phi, lengths, gamma0, pi0=None, n_states=None, spl=0, gemm=0, fb_classic=0, exact_stop=True, **kw):
+def run_gpu(fea, Phi, lengths, gamma0, pi0=None, n_states=None, spl=0, gemm=0, fb_classic=0, exact_stop=True, fb_split=0, **kw):
     from vbx_b200.batch import VbxBatch
     import vbx_b200._lib as L
     lengths = np.asarray(lengths)
     S_user = gamma0.shape[1]
     ns = np.full(len(lengths), S_user, dtype=np.int32) if n_states is None else np.asarray(n_states, dtype=np.int32)
-    vb = VbxBatch(lengths, fea.shape[1], ns, device=dev(), exact_stop=exact_stop)
+    if spl or fb_classic:
+        fb_split = 2                  # these knobs belong to the fused sweep
+    vb = VbxBatch(lengths, fea.shape[1], ns, device=dev(), exact_stop=exact_stop, fb_split=fb_split)
     vb.workspace.fill_(0xFF)       # poison (NaN in float32 and float64): nothing may be read before it is written
     if spl:
         vb.set_option('fb_states_per_lane', spl)
@@ -85,18 +87,20 @@ def run_gpu(fea, Phi, lengths, gamma0, pi0=None, n_states=None, spl=0, gemm=0, f
     return res
 
 
+@pytest.mark.parametrize('fb', [2, 1], ids=['fused', 'split'])
 @pytest.mark.parametrize('gemm', [0, 1], ids=['mma3xtf32', 'ffma'])
 @pytest.mark.parametrize('tag', sorted(CASES))
-def test_reference_goldens(tag, gemm):
-    """Every reference-generated case through both contraction modes: tensor cores in split-precision 3xTF32 (the
-    batch default) and float32 FFMA (the default of the drop-in VBx(), tighter)."""
+def test_reference_goldens(tag, gemm, fb):
+    """Every reference-generated case through both contraction modes - tensor cores in split-precision 3xTF32 (the
+    batch default) and float32 FFMA (the default of the drop-in VBx(), tighter) - and both forward-backward schedules:
+    the fused sweep (large batches) and forward / backward on separate warps + combine pass (small batches)."""
     c = CASES[tag]
     T = c['fea'].shape[0]
     kw = dict(Fa=float(c['Fa']), Fb=float(c['Fb']), loopProb=float(c['loopProb']), maxIters=int(c['maxIters']),
               epsilon=float(c['epsilon']))
     if 'alpha0' in c:
         kw.update(alpha0=c['alpha0'][None], invL0=c['invL0'][None])
-    out = run_gpu(c['fea'], c['Phi'], [T], c['gamma0'], pi0=c['pi0'], gemm=gemm, **kw)
+    out = run_gpu(c['fea'], c['Phi'], [T], c['gamma0'], pi0=c['pi0'], gemm=gemm, fb_split=fb, **kw)
     n = int(out['n_iters'][0])
     # identical iteration counts in both modes: the stop test of VBx/VBx.py:122 is decided on float64 ELBO values
     # (vbx_exact64.cu) whenever the float32 ELBO step is not safely away from epsilon ('early_stop': epsilon = 1e-3
@@ -123,11 +127,12 @@ def es_inputs():
     return z, q
 
 
-def test_es2005a_fixed_iterations():
+@pytest.mark.parametrize('fb', [2, 1], ids=['fused', 'split'])
+def test_es2005a_fixed_iterations(fb):
     """Config 1: the real recording, same 13 iterations as the reference (VBx/vbhmm.py:154-158)."""
     z, q = es_inputs()
     out = run_gpu(z['fea'], z['Phi'], [q.shape[0]], q, Fa=float(z['Fa']), Fb=float(z['Fb']),
-                  loopProb=float(z['loopProb']), maxIters=13, epsilon=-np.inf)
+                  loopProb=float(z['loopProb']), maxIters=13, epsilon=-np.inf, fb_split=fb)
     assert np.abs(out['gamma'] - z['gamma']).max() <= G_TOL
     assert np.abs(out['pi'][0] - z['pi']).max() <= PI_TOL
     check_elbo(out['Li'][0], z['Li'])
@@ -213,21 +218,24 @@ def test_classic_forward_backward_sweep(tag):
     check_elbo(classic['Li'][0], ahead['Li'][0])
 
 
+@pytest.mark.parametrize('fb', [2, 1], ids=['fused', 'split'])
 @pytest.mark.parametrize('S', [3, 4, 8, 10, 16, 31, 32, 64])
-def test_state_counts_vs_oracle(S):
+def test_state_counts_vs_oracle(S, fb):
     lens, d = ragged_batch(9, S, seed=30 + S, tmax=400)
     ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(S, 1.0 / S),
                               0.2, 6.0, 0.35, 6, -np.inf)
-    out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=0.2, Fb=6.0, loopProb=0.35, maxIters=6, epsilon=-np.inf)
+    out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=0.2, Fb=6.0, loopProb=0.35, maxIters=6, epsilon=-np.inf, fb_split=fb)
     assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
     assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
     check_elbo(out['Li'], ref['Li'])
 
 
+@pytest.mark.parametrize('fb', [2, 1], ids=['chunked_scan', 'split'])
 @pytest.mark.parametrize('S', [6, 16, 30, 64])
-def test_long_recordings_chunked_scan(S):
-    """Recordings of >= 4096 frames take the chunked-scan forward-backward (three phases per sweep); mixed with short
-    ones in the same batch.  Same parity bar against the oracle."""
+def test_long_recordings_chunked_scan(S, fb):
+    """Recordings of >= 4096 frames: inside a large batch they take the chunked-scan forward-backward (three phases per
+    sweep), in a small batch the concurrent forward / backward sweeps; mixed with short ones in the same batch.  Same
+    parity bar against the oracle."""
     lens = np.array([4096, 300, 5000, 4097, 1, 9000 if S <= 16 else 4500])
     d = synth.make_batch(lens, R=128, S=S, seed=90 + S, dtype=np.float32)
     ns = np.full(len(lens), S, dtype=np.int32)
@@ -241,15 +249,40 @@ def test_long_recordings_chunked_scan(S):
         pi0[b, :ns[b]] = 1.0 / ns[b]
     kw = dict(Fa=0.2, Fb=6.0, loopProb=0.35) if S == 30 else dict(Fa=0.3, Fb=17.0, loopProb=0.99)
     ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], g0, pi0, kw['Fa'], kw['Fb'], kw['loopProb'], 6, -np.inf, n_states=ns)
-    out = run_gpu(d['fea'], d['Phi'], lens, g0.astype(np.float32), n_states=ns, maxIters=6, epsilon=-np.inf, **kw)
+    out = run_gpu(d['fea'], d['Phi'], lens, g0.astype(np.float32), n_states=ns, maxIters=6, epsilon=-np.inf, fb_split=fb, **kw)
     assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
     assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
     check_elbo(out['Li'], ref['Li'])
     assert np.abs(out['gamma'].sum(1) - 1).max() < 1e-5
     # a long recording alone == inside the batch, bit for bit
     lo, hi = d['offsets'][0], d['offsets'][1]
-    one = run_gpu(d['fea'][lo:hi], d['Phi'], [hi - lo], g0[lo:hi].astype(np.float32), maxIters=6, epsilon=-np.inf, **kw)
+    one = run_gpu(d['fea'][lo:hi], d['Phi'], [hi - lo], g0[lo:hi].astype(np.float32), maxIters=6, epsilon=-np.inf, fb_split=fb, **kw)
     assert np.array_equal(one['gamma'], out['gamma'][lo:hi]) and np.array_equal(one['Li'][0], out['Li'][0])
+
+
+@pytest.mark.parametrize('name,B,T,S,iters,hp,fb', [
+    ('config2_headline_shape', 48, 1000, 16, 10, (0.3, 17.0, 0.99), 2),
+    ('config2_small_batch', 48, 1000, 16, 10, (0.3, 17.0, 0.99), 1),
+    ('config3_ragged_20_iterations', 48, (200, 3000), 16, 20, (0.3, 17.0, 0.99), 2),
+    ('config4_long_40_iterations_chunked', 3, 12000, 30, 40, (0.2, 6.0, 0.35), 2),
+    ('config4_long_40_iterations_split', 3, 12000, 30, 40, (0.2, 6.0, 0.35), 1),
+    ('config5_s64', 6, 2000, 64, 10, (0.3, 17.0, 0.99), 2),
+])
+def test_baseline_configs_at_their_sizes(name, B, T, S, iters, hp, fb):
+    """BASELINE.json's configs at their own recording length, state count and ITERATION count (error growth over 20-40
+    float32 iterations included), a sample of recordings each, against the float64 oracle; bench.py repeats this check on
+    recordings of the full-size batch it times."""
+    rng = np.random.default_rng(len(name))
+    lens = rng.integers(T[0], T[1] + 1, size=B) if isinstance(T, tuple) else np.full(B, T)
+    d = synth.make_batch(lens, R=128, S=S, seed=400 + B + S, dtype=np.float32)
+    Fa, Fb, lp = hp
+    ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(S, 1.0 / S), Fa, Fb, lp, iters, -np.inf)
+    out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=Fa, Fb=Fb, loopProb=lp, maxIters=iters, epsilon=-np.inf, fb_split=fb)
+    assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
+    assert np.abs(out['pi'] - ref['pi']).max() <= PI_TOL
+    check_elbo(out['Li'], ref['Li'])
+    assert np.array_equal(out['gamma'].argmax(1), ref['gamma'].argmax(1)) or \
+        (out['gamma'].argmax(1) != ref['gamma'].argmax(1)).mean() < 1e-3
 
 
 def test_small_feature_dims():

@@ -22,11 +22,12 @@ def _ptr(t):
 class VbxBatch:
     """Plan + workspace for one packed ragged batch on one device."""
 
-    def __init__(self, lengths, R, n_states, device=None, allocate=True, exact_stop=True):
+    def __init__(self, lengths, R, n_states, device=None, allocate=True, exact_stop=True, fb_split=0):
         """lengths: per-recording frame counts T_b; R: feature dim seen by VBx() (VBx/VBx.py:74);
         n_states: int or per-recording ints (the `pi`-as-int / len(pi) of VBx/VBx.py:76-77).
         exact_stop: reserve the buffers of the float64 finishing phase, so that run() with a finite epsilon applies the
-        reference's stop rule (VBx/VBx.py:122-125) at float64 resolution; False = float32 only (smaller workspace)."""
+        reference's stop rule (VBx/VBx.py:122-125) at float64 resolution; False = float32 only (smaller workspace).
+        fb_split: 0 = auto, 1 = always, 2 = never run the forward / backward sweeps concurrently (include/vbx_b200.h)."""
         if not torch.cuda.is_available():
             raise VbxError('vbx_b200 needs a CUDA device (B200, sm_100); there is no CPU path')
         self.lib = _lib.load()
@@ -54,6 +55,7 @@ class VbxBatch:
             raise VbxError(f'vbx_create failed ({rc}): no usable sm_100 device')
         self.exact_stop = bool(exact_stop)
         self._check(self.lib.vbx_set_option(self._h, b'exact_stop', int(self.exact_stop)))
+        self._check(self.lib.vbx_set_option(self._h, b'fb_split', int(fb_split)))
         need = ctypes.c_size_t()
         self._check(self.lib.vbx_plan(self._h, self.offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                                       self.B, self.R, self.S, ctypes.byref(need)))

@@ -25,6 +25,8 @@ struct vbx_handle_s {
     int opt_projection = 0;
     int opt_timing = 0;
     int opt_gemm = 0;  // 0 = mma.sync 3xTF32, 1 = FFMA
+    int opt_debug_sync = 0;      // 1 = synchronise after every launch group and name it on stderr (debugging aid)
+    int opt_fb_split = 0;        // 0 = auto (few recordings: sweeps on separate warps), 1 = always, 2 = never
     int opt_exact_stop = 1;      // 1 = finish recordings in float64 once the ELBO step nears epsilon (vbx_exact64.cu)
     int opt_noise_c = 2;         // float32 noise bound of an ELBO difference = noise_c * 2^-24 * |ELBO|
     int opt_guard_mult = 16;     // a recording switches when its ELBO step < epsilon + guard_mult * noise bound
@@ -112,6 +114,12 @@ size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
     w.active = c.take<int32_t>(B);
     w.scratch = c.take<float>(2 * vbx::kMaxS);
     if (pl.R == 128) w.tc_scratch = c.take<float>(vbx::tc_scratch_floats());
+    if (pl.split) {
+        w.ahat = c.take<float>(N * S);
+        w.bhat = c.take<float>(N * S);
+        w.socc = c.take<float>((size_t)pl.n_mtiles * S);
+        w.sent = c.take<float>((size_t)pl.n_mtiles * S);
+    }
     {
         const size_t LC = (size_t)pl.n_lchunks;
         w.fa_u = c.take<float>(LC * S * S);
@@ -199,6 +207,15 @@ int vbx_set_option(vbx_handle_t h, const char *name, int32_t value) {
         h->opt_gemm = value;
         return VBX_OK;
     }
+    if (!strcmp(name, "debug_sync")) {
+        h->opt_debug_sync = value ? 1 : 0;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "fb_split")) {   // takes effect at the next vbx_plan
+        if (value < 0 || value > 2) return fail(h, VBX_ERR_ARG, "fb_split must be 0 (auto), 1 (always) or 2 (never)");
+        h->opt_fb_split = value;
+        return VBX_OK;
+    }
     if (!strcmp(name, "exact_stop")) {   // takes effect at the next vbx_plan (workspace layout)
         h->opt_exact_stop = value ? 1 : 0;
         return VBX_OK;
@@ -263,9 +280,18 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
         }
     }
     mbegin[n_rec] = (int32_t)mrec.size();
-    // long recordings -> chunk lists of the chunked-scan forward-backward
+    // Few recordings cannot fill the GPU with one warp-group each: run the forward and the backward sweep of every
+    // recording concurrently on separate warps (vbx_fb_split.cu).  Auto: when the sweeps of the fused kernel would occupy
+    // at most two warps per SM.
+    bool split = h->opt_fb_split == 1;
+    if (h->opt_fb_split == 0) {
+        const int spl = S >= 16 ? 2 : 1, rpw = 32 / (S / spl);
+        const int warps = (n_rec + rpw - 1) / rpw;
+        split = warps <= 2 * 148;
+    }
+    // long recordings -> chunk lists of the chunked-scan forward-backward (not needed by the split sweeps)
     std::vector<int32_t> lrec_list, lrec_first(std::max(n_rec, 1), 0), lrec_nchunks(std::max(n_rec, 1), 0), lchunk_rec, lchunk_idx;
-    for (int b = 0; b < n_rec; ++b) {
+    for (int b = 0; b < n_rec && !split; ++b) {
         const int64_t T = offsets_host[b + 1] - offsets_host[b];
         if (T >= vbx::kLongT) {
             const int K = (int)((T + vbx::kChunk - 1) / vbx::kChunk);
@@ -328,6 +354,7 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
     pl.R = R;
     pl.S = S;
     pl.exact = h->opt_exact_stop;
+    pl.split = split ? 1 : 0;
     pl.n_frames = n_rec ? offsets_host[n_rec] : 0;
     pl.n_ltiles = (int32_t)lrec.size();
     pl.n_mtiles = (int32_t)mrec.size();
@@ -375,6 +402,14 @@ static int check_ready(vbx_handle_t h, const char *who) {
 static int counted(vbx_handle_t h, int n, const char *what) {
     if (n < 0) return cuda_fail(h, cudaGetLastError(), what);
     h->launches += n;
+    if (h->opt_debug_sync) {
+        fprintf(stderr, "[vbx_b200] %s: %d launch(es) ...", what, n);
+        fflush(stderr);
+        const cudaError_t e = cudaDeviceSynchronize();
+        fprintf(stderr, " %s\n", cudaGetErrorString(e));
+        fflush(stderr);
+        if (e != cudaSuccess) return cuda_fail(h, e, what);
+    }
     return VBX_OK;
 }
 // Brackets one kernel class with a pair of events on `st` when timing is enabled.

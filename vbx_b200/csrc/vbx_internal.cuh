@@ -22,6 +22,7 @@ constexpr int kTcMaxD = 2048;  // largest raw dimension of the tcgen05 front end
 struct Plan {
     int32_t n_rec = 0, R = 0, S = 0;
     int32_t exact = 0;                  // 1 = the workspace holds the buffers of the float64 finishing phase
+    int32_t split = 0;                  // 1 = forward and backward sweeps on separate warps + combine pass (vbx_fb_split.cu)
     int64_t n_frames = 0;
     int32_t n_ltiles = 0, n_mtiles = 0;
     int64_t max_T = 0;
@@ -73,6 +74,9 @@ struct Workspace {
     double *reg64 = nullptr;     // [n_rec]
     double *pi64 = nullptr;      // [n_rec,S]
     float *scratch = nullptr;  // [2*kMaxS] write sink for warp lanes that own no recording
+    // split forward-backward (vbx_fb_split.cu); null unless the plan chose it
+    float *ahat = nullptr, *bhat = nullptr;   // [N,S] normalised forward variables / self-scaled backward variables
+    float *socc = nullptr, *sent = nullptr;   // [n_mtiles,S] per-tile sums of gamma / of the re-entry terms of eq. (24)
     float *tc_scratch = nullptr; // operand images of the tcgen05 front end (vbx_project_tc.cu); null unless R == 128
     // chunked scan of long recordings: per (chunk, basis) operators and per-chunk boundary vectors / partial sums
     float *fa_u = nullptr, *fa_lam = nullptr, *fa_exp = nullptr, *astart = nullptr;   // [LC,S,S], [LC,S] mantissa, [LC,S] exponent, [LC,S]
@@ -181,6 +185,9 @@ int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
                             int spl, int classic, cudaStream_t st);
 int launch_elbo_trace(const Plan &pl, const double *Li, int max_iters, double *out, cudaStream_t st);
+// forward and backward sweeps on separate warps + combine pass, any recording length (vbx_fb_split.cu)
+int launch_forward_backward_split(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
+                                  const int32_t *n_states, cudaStream_t st);
 // chunked-scan forward-backward for long recordings (vbx_long_kernels.cu)
 int launch_forward_backward_long(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                                  const int32_t *n_states, cudaStream_t st);

@@ -1327,6 +1327,12 @@ int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
                             int spl, int classic, cudaStream_t st) {
     if (pl.n_rec == 0) return 0;
+    if (pl.split) {
+        const int rs = launch_forward_backward_split(pl, ws, rp, gamma, pi, n_states, st);
+        if (rs < 0) return rs;
+        elbo_kernel<<<pl.n_rec, 128, 0, st>>>(pl, ws, rp, Li, n_iters, flags, iter);
+        return cudaGetLastError() == cudaSuccess ? rs + 1 : -1;
+    }
     int rc = -1;
 #define VBX_FB(S_, L_) rc = launch_fb_t<S_, L_>(pl, ws, rp, gamma, pi, n_states, classic != 0, st)
     const int S = pl.S;
