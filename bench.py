@@ -509,6 +509,8 @@ def main():
     ap.add_argument('--projection', type=int, default=0)
     ap.add_argument('--fb-classic', type=int, default=0, help='1 = normalise-every-frame forward-backward sweep (A/B against the look-ahead kernel)')
     ap.add_argument('--opt', action='append', default=[], help='name=value passed to vbx_set_option (A/B runs)')
+    ap.add_argument('--parts', type=int, default=0, help='sub-batches on separate streams (vbx_b200/parts.py): 0 = auto, 1 = off')
+    ap.add_argument('--fb-split', type=int, default=0, help='0 = auto, 1 = always, 2 = never: forward / backward sweeps on separate warps')
     ap.add_argument('--front', default='project', choices=['project', 'xvectors'],
                     help="what feeds the EM loop: 'project' = rho = X.V (the headline definition, SURVEY 8d); 'xvectors' = the "
                          "real-data chain vbx_prepare_xvectors (x-vector transform + PLDA projection, two tcgen05 passes)")
@@ -526,6 +528,7 @@ def main():
     from vbx_b200 import shard
     from vbx_b200.batch import VbxBatch
     from vbx_b200.host_pipeline import HostPipeline
+    from vbx_b200.parts import make_batch, PartitionedBatch
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -555,17 +558,23 @@ def main():
             data = make_device_batch(lengths, w['S'], seed=17 + rank, device=device)
         N = int(lengths.sum())
         dbg(f'{wname}: data on device, {len(lengths)} recordings, N={N}')
-        vb = VbxBatch(lengths, R_DIM, w['S'], device=device)
-        if args.fb_spl:
-            vb.set_option('fb_states_per_lane', args.fb_spl)
-        if args.projection:
-            vb.set_option('projection', args.projection)
-        if args.fb_classic:
-            vb.set_option('fb_classic', 1)
-        for kv in args.opt:
-            k, _, v = kv.partition('=')
-            vb.set_option(k, int(v))
-        vb.set_option('timing', 1)
+        def configure(b, timing):
+            if args.fb_spl:
+                b.set_option('fb_states_per_lane', args.fb_spl)
+            if args.projection:
+                b.set_option('projection', args.projection)
+            if args.fb_classic:
+                b.set_option('fb_classic', 1)
+            for kv in args.opt:
+                k, _, v = kv.partition('=')
+                b.set_option(k, int(v))
+            b.set_option('timing', int(timing))
+
+        vb = make_batch(lengths, R_DIM, w['S'], device=device, parts=args.parts, fb_split=args.fb_split)
+        partitioned = isinstance(vb, PartitionedBatch)
+        # per-kernel CUDA events are only meaningful when the kernels of a step run one after the other: with the batch
+        # split over two streams they are taken in a separate serial pass below
+        configure(vb, timing=not partitioned)
         in_library_collective = vb.attach_comm() if world > 1 else False
         S = vb.S
         rho = torch.empty((N, R_DIM), dtype=torch.float32, device=device)
@@ -641,13 +650,37 @@ def main():
             N_total = N
         timings = vb.timings(reset=True)
         launches = (vb.launches - l0) / steps
+        kernel_pass = 'in the timed region'
+        if partitioned:
+            gamma_keep, pi_keep, out_keep = gamma.clone(), pi.clone(), {k: v.clone() for k, v in out.items() if k in ('Li', 'n_iters')}
+            serial = VbxBatch(lengths, R_DIM, w['S'], device=device, fb_split=args.fb_split)
+            configure(serial, timing=True)
+            serial.n_states = vb.n_states
+            whole_vb, vb = vb, serial
+            for i in range(2 + 3):
+                if i == 2:
+                    torch.cuda.synchronize()
+                    serial.timings(reset=True)
+                if flush is not None:
+                    flush.zero_()
+                step()
+            torch.cuda.synchronize()
+            timings = {k: (ms * steps / 3.0, n * steps / 3.0) for k, (ms, n) in serial.timings(reset=True).items()}
+            vb = whole_vb
+            serial.close()
+            gamma.copy_(gamma_keep)
+            pi.copy_(pi_keep)
+            out = dict(out, **out_keep)
+            kernel_pass = ('separate serial pass of 3 steps (one stream); the step time itself has the two halves of the batch '
+                           'overlapping on two streams, so these per-kernel times add up to more than ms_per_step')
         tr = trace.cpu().numpy()
         assert np.all(np.isfinite(tr)), 'non-finite ELBO in the benchmark run'
         n_all = world * w['B'] if not strong else w['B']
         assert np.all(tr[w['iters']:] == n_all), (tr[w['iters']:], n_all)       # every recording of the job ran every iteration
         return dict(ms=ms, N=N, N_total=N_total, timings=timings, launches=launches, clocks=clocks, lengths=lengths,
                     data=data, vb=vb, S=S, out=out, steps=steps, strong=strong, trace=tr, gamma=gamma, pi=pi,
-                    in_library_collective=bool(in_library_collective))
+                    in_library_collective=bool(in_library_collective), partitioned=partitioned, kernel_pass=kernel_pass,
+                    parts=len(vb.children) if partitioned else 1)
 
     def parity_sample(res, w, n_rec=3):
         """Size-true check inside the bench: a few recordings of THIS batch against the float64 C oracle (the checker)."""
@@ -801,7 +834,8 @@ def main():
             'data': 'synthetic (seeded sticky-Markov speakers in PLDA space, SURVEY.md 8d; generated on the device)',
             'config': workload_config(w, wname, world),
             'target': {'north_star_x_vectors_per_s': 1e7, 'ratio': value / 1e7 / max(world, 1)},
-            'roofline': roof, 'whole_step': whole, 'kernels': per_kernel, 'gpu_launches': res['launches'] * args.steps,
+            'roofline': roof, 'whole_step': whole, 'kernels': per_kernel, 'kernels_measured': res['kernel_pass'],
+            'sub_batches_on_streams': res['parts'], 'gpu_launches': res['launches'] * args.steps,
             'gpu_launches_per_step': res['launches'], 'clocks': res['clocks'], 'e2e': e2e, 'cpu_baseline': cpu, 'parity': parity,
             'elbo_trace': {'sum_per_iteration': [float(x) for x in res['trace'][:w['iters']]], 'recordings': int(res['trace'][w['iters']]),
                            'collective': ('ncclAllReduce inside vbx_elbo_trace (communicator attached with vbx_attach_comm)' if res['in_library_collective']

@@ -286,6 +286,42 @@ def test_baseline_configs_at_their_sizes(name, B, T, S, iters, hp, fb):
         (out['gamma'].argmax(1) != ref['gamma'].argmax(1)).mean() < 1e-3
 
 
+def test_partitioned_batch_equals_the_whole_batch():
+    """vbx_b200.parts: two sub-batches on two streams give bit-identical results to one batch (recordings are independent),
+    through the projection, both stop-rule phases, hard labels and the ELBO trace."""
+    from vbx_b200.batch import VbxBatch
+    from vbx_b200.parts import make_batch, PartitionedBatch
+    S = 7
+    lens, d = ragged_batch(41, S, seed=99, tmax=500)
+    dd = synth.make_batch(lens, R=128, S=S, seed=99, D=256, dtype=np.float32)
+    ns = np.full(len(lens), S, dtype=np.int32)
+    ns[5] = 3
+    g0 = dd['gamma0'].astype(np.float32).copy()
+    lo, hi = dd['offsets'][5], dd['offsets'][6]
+    g0[lo:hi, 3:] = 0
+    g0[lo:hi] /= g0[lo:hi].sum(1, keepdims=True)
+    results = []
+    for parts in (1, 2, 3):
+        vb = make_batch(lens, 128, ns, device=dev(), parts=parts)
+        assert isinstance(vb, PartitionedBatch) == (parts > 1)
+        g = torch.zeros((int(lens.sum()), vb.S), device=dev())
+        g[:, :S] = cuda(g0)
+        p = torch.zeros((len(lens), vb.S), device=dev())
+        for b in range(len(lens)):
+            p[b, :ns[b]] = 1.0 / ns[b]
+        rho = vb.prepare_project(cuda(dd['X']), cuda(dd['V']), cuda(dd['Phi']))
+        out = vb.run(g, p, Fa=0.3, Fb=17.0, loopProb=0.99, maxIters=25, epsilon=1e-5, return_model=True)
+        lab = vb.hard_labels(g)
+        tr = vb.elbo_trace(out['Li'])
+        torch.cuda.synchronize()
+        results.append([t.cpu().numpy() for t in (rho, g, p, out['Li'], out['n_iters'], out['flags'], out['alpha'], lab, tr)])
+        vb.close()
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert np.array_equal(a, b, equal_nan=True)
+    assert len(set(results[0][4].tolist())) > 1          # recordings stopped at different iterations
+
+
 def test_small_feature_dims():
     for R in (16, 32, 64):
         lens, d = ragged_batch(6, 5, seed=50 + R, tmax=200, R=R)

@@ -22,7 +22,7 @@ def _ptr(t):
 class VbxBatch:
     """Plan + workspace for one packed ragged batch on one device."""
 
-    def __init__(self, lengths, R, n_states, device=None, allocate=True, exact_stop=True, fb_split=0):
+    def __init__(self, lengths, R, n_states, device=None, allocate=True, exact_stop=True, fb_split=0, S_pad=None):
         """lengths: per-recording frame counts T_b; R: feature dim seen by VBx() (VBx/VBx.py:74);
         n_states: int or per-recording ints (the `pi`-as-int / len(pi) of VBx/VBx.py:76-77).
         exact_stop: reserve the buffers of the float64 finishing phase, so that run() with a finite epsilon applies the
@@ -47,7 +47,7 @@ class VbxBatch:
         if ns.shape[0] != self.B:
             raise ValueError('n_states must be an int or one int per recording')
         self.n_states_host = ns
-        self.S = _lib.padded_states(int(ns.max()) if self.B else 1)
+        self.S = _lib.padded_states(int(ns.max()) if self.B else 1) if S_pad is None else int(S_pad)
         self.uniform_states = bool(np.all(ns == self.S))
         self._h = ctypes.c_void_p()
         rc = self.lib.vbx_create(self.device.index, ctypes.byref(self._h))
@@ -133,7 +133,7 @@ class VbxBatch:
     def hard_labels(self, gamma, second=False):
         """VBx/vbhmm.py:160-162 on the device: the most likely speaker per frame (int32 [N]); with second=True also
         the runner-up.  Only these labels need to leave the GPU, not gamma."""
-        self._f32(gamma, (self.N, self.S), 'gamma')
+        self._f32(gamma, (self.N, self.S), 'gamma', need_workspace=False)
         first = torch.empty(self.N, dtype=torch.int32, device=self.device)
         sec = torch.empty(self.N, dtype=torch.int32, device=self.device) if second else None
         self._check(self.lib.vbx_hard_labels(self._h, _ptr(gamma), _ptr(self.n_states), _ptr(first), _ptr(sec), self._stream()))
@@ -154,8 +154,8 @@ class VbxBatch:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _f32(self, t, shape, name):
-        if self.workspace is None:
+    def _f32(self, t, shape, name, need_workspace=True):
+        if need_workspace and self.workspace is None:
             raise VbxError('no workspace bound (VbxBatch(..., allocate=False) needs bind())')
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError(f'{name}: expected a contiguous float32 CUDA tensor')

@@ -98,6 +98,7 @@ size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
     w.p = c.take<float>(N * S);
     w.rowmax = c.take<float>(N);
     w.rsigma = c.take<float>(N);
+    w.cvec = c.take<float>(N);
     w.partial = c.take<float>((size_t)pl.n_mtiles * S * R);
     w.A = c.take<float>(B * S * R);
     {
@@ -584,7 +585,7 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
             if (rc) return rc;
             {
                 Timed t(h, st, VBX_K_LOGLIK);
-                rc = counted(h, h->opt_gemm ? vbx::launch_loglik(pl, h->ws, rho, st) : vbx::launch_loglik_mma(pl, h->ws, rho, st), "loglik");
+                rc = counted(h, h->opt_gemm ? vbx::launch_loglik(pl, h->ws, rho, pi_io, n_states, rp.loopP, st) : vbx::launch_loglik_mma(pl, h->ws, rho, pi_io, n_states, rp.loopP, st), "loglik");
             }
             if (rc) return rc;
             {

@@ -31,6 +31,12 @@ __device__ __forceinline__ float gsum(float v) {
     for (int off = LANES / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
 }
+// index shuffle pinned in program order (see vbx_kernels.cu: keeps each hand-out of a per-frame scalar inside its step)
+__device__ __forceinline__ float shfl_pin(const float v, const int src) {
+    float r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=f"(r) : "f"(v), "r"(src));
+    return r;
+}
 __device__ __forceinline__ float rcpf(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -116,7 +122,10 @@ __global__ void __launch_bounds__(128) fb_sweeps_kernel(Plan pl, Workspace ws, R
     }
     // groups without a recording read row 0 of the batch and write into a scratch row (stride 0): no predicates in the loops
     const float *pp = ws.p + f0 * S_PAD + l * SPL;
+    const float *cv = ws.cvec + f0;         // c_t = p_t . w from the log-likelihood kernel
     const int64_t ostr = live ? S_PAD : 0;
+    const int gl0 = lane - l;               // first lane of this group
+    constexpr int NC = (PF + LPR - 1) / LPR; // per burst every lane keeps NC of the c values, handed out by shuffle
 
     if (!backward) {
         // ---------------- forward sweep, VBx/VBx.py:164,167-168 (look-ahead recurrences, see vbx_kernels.cu) ----------------
@@ -126,18 +135,17 @@ __global__ void __launch_bounds__(128) fb_sweeps_kernel(Plan pl, Workspace ws, R
         float y[SPL];
         const Vec<SPL> p0 = ldg_vec<SPL>(pp);
         const Vec<SPL> p1 = ldg_vec<SPL>(pp + (int64_t)min(1, Tlast) * S_PAD);
-        float loc = 0.f, locq = 0.f, locc = 0.f;
+        float loc = 0.f, locq = 0.f;
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
             const int s = l * SPL + k;
             y[k] = (live && s < ns) ? p0.v[k] * (pi[k] + VBX_EPS_TR) : 0.f;   // VBx/VBx.py:164
             loc += y[k];
             locq = fmaf(p1.v[k], y[k], locq);
-            locc = fmaf(p1.v[k], w[k], locc);
         }
         float Yc = gsum<LPR>(loc);     // Y_0 = sigma_0
         float q = gsum<LPR>(locq);     // q_0 = p_1 . y_0
-        float c = gsum<LPR>(locc);     // c_1 = p_1 . w
+        float c = __ldg(cv + min(1, Tlast));   // c_1 = p_1 . w
         float rn = 1.f;                 // r_1
         float rs1 = rcpf(Yc);           // 1/sigma_0 (becomes r_2)
         {
@@ -147,17 +155,15 @@ __global__ void __launch_bounds__(128) fb_sweeps_kernel(Plan pl, Workspace ws, R
             st_vec<SPL>(ah, an);
             if (l == 0) rs[0] = rs1;
         }
-        auto fstep = [&](const int j, const Vec<SPL> &ps, const Vec<SPL> &pn, const bool check) {
+        auto fstep = [&](const int j, const Vec<SPL> &ps, const Vec<SPL> &pn, const float cn, const bool check) {
             const int s = j + 1;
-            float ys[SPL], lq = 0.f, lc = 0.f;
+            float ys[SPL], lq = 0.f;
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
                 ys[k] = (rn * ps.v[k]) * fmaf(P, y[k], w[k] * Yc);
                 lq = fmaf(pn.v[k], ys[k], lq);
-                lc = fmaf(pn.v[k], w[k], lc);
             }
             const float qn = gsum<LPR>(lq);                    // consumed by the NEXT step
-            const float cn = gsum<LPR>(lc);
             const float Ys = rn * fmaf(P, q, c * Yc);           // Y_s = sum_i y_s,i
             const float inv = rcpf(Ys);
             const float rsig = rn * Yc * inv;                   // 1 / sigma_s
@@ -178,26 +184,32 @@ __global__ void __launch_bounds__(128) fb_sweeps_kernel(Plan pl, Workspace ws, R
             }
         };
         Vec<SPL> bufA[PF], bufB[PF];
+        float cbA[NC], cbB[NC];             // lane l keeps c of the frames (burst start) + k LPR + l
         Vec<SPL> ps = p1;
-        auto fchunk = [&](const int j0, Vec<SPL>(&cur)[PF], Vec<SPL>(&nxt)[PF], const bool check) {
+        // slot i of a burst starting at step j0 holds the row (and c) of frame j0 + i + 2
+        auto fchunk = [&](const int j0, Vec<SPL>(&cur)[PF], Vec<SPL>(&nxt)[PF], const float (&cc)[NC], float (&nc)[NC], const bool check) {
 #pragma unroll
             for (int i = 0; i < PF; ++i) nxt[i] = ldo<SPL>(pp + (int64_t)min(j0 + PF + i + 2, Tlast) * S_PAD);
 #pragma unroll
+            for (int k = 0; k < NC; ++k) nc[k] = ldo<1>(cv + min(j0 + PF + 2 + k * LPR + l, Tlast)).v[0];
+#pragma unroll
             for (int i = 0; i < PF; ++i) {
-                fstep(j0 + i, ps, cur[i], check);
+                fstep(j0 + i, ps, cur[i], shfl_pin(cc[i / LPR], gl0 + i % LPR), check);
                 ps = cur[i];
             }
         };
 #pragma unroll
         for (int i = 0; i < PF; ++i) bufA[i] = ldg_vec<SPL>(pp + (int64_t)min(i + 2, Tlast) * S_PAD);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) cbA[k] = __ldg(cv + min(2 + k * LPR + l, Tlast));
         int j0 = 0;
         for (; j0 + 2 * PF <= Tmin - 1; j0 += 2 * PF) {
-            fchunk(j0, bufA, bufB, false);
-            fchunk(j0 + PF, bufB, bufA, false);
+            fchunk(j0, bufA, bufB, cbA, cbB, false);
+            fchunk(j0 + PF, bufB, bufA, cbB, cbA, false);
         }
         for (; j0 < Tmax - 1; j0 += 2 * PF) {
-            fchunk(j0, bufA, bufB, true);
-            fchunk(j0 + PF, bufB, bufA, true);
+            fchunk(j0, bufA, bufB, cbA, cbB, true);
+            fchunk(j0 + PF, bufB, bufA, cbB, cbA, true);
         }
     } else {
         // ---------------- backward sweep, VBx/VBx.py:165,170-171 (self-scaled look-ahead recurrences) ----------------
@@ -215,30 +227,24 @@ __global__ void __launch_bounds__(128) fb_sweeps_kernel(Plan pl, Workspace ws, R
         float dprev = 1.f, e = 0.f, f;
         float rho0 = 1.f, rho1 = 1.f, rho2 = 1.f;   // rho_t (forms kappa_{t+1} of the running step), rho_{t-1}, rho_{t-2}
         const Vec<SPL> plast = ldg_vec<SPL>(pp + (int64_t)Tlast * S_PAD);
-        {
-            float locf = 0.f;
 #pragma unroll
-            for (int k = 0; k < SPL; ++k) {
-                b[k] = 1.f;
-                kap[k] = plast.v[k];                 // rho_{T-2} = 1
-                locf = fmaf(w[k], kap[k], locf);
-            }
-            f = gsum<LPR>(locf);
+        for (int k = 0; k < SPL; ++k) {
+            b[k] = 1.f;
+            kap[k] = plast.v[k];                     // rho_{T-2} = 1
         }
-        // step ii handles frame t = T-2-ii with pt = p_t (row of frame t, needed for kappa_t)
-        auto bstep = [&](const int ii, const Vec<SPL> &pt, const bool check) {
+        f = __ldg(cv + Tlast);                       // f_{T-1} = w . kappa_{T-1} = c_{T-1}
+        // step ii handles frame t = T-2-ii with pt = p_t (row of frame t, needed for kappa_t) and ct = c_t = p_t . w
+        auto bstep = [&](const int ii, const Vec<SPL> &pt, const float ct, const bool check) {
             const int t = T - 2 - ii;
-            float v[SPL], kapn[SPL], loce = 0.f, locf = 0.f;
+            float v[SPL], kapn[SPL], loce = 0.f;
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
                 v[k] = kap[k] * b[k];                               // v_t
                 kapn[k] = rho1 * pt.v[k];                           // kappa_t = rho_{t-1} p_t
-                const float wk = w[k] * kapn[k];
-                loce = fmaf(wk, v[k], loce);
-                locf += wk;
+                loce = fmaf(w[k] * kapn[k], v[k], loce);
             }
             const float en = gsum<LPR>(loce);                       // e_t, consumed by the NEXT step
-            const float fn = gsum<LPR>(locf);                       // f_t
+            const float fn = rho1 * ct;                             // f_t = w . kappa_t (no reduction: c is precomputed)
             const float d = fmaf(P, e, dprev * f);                  // d_t = w . v_t
             float bn[SPL];
 #pragma unroll
@@ -259,23 +265,28 @@ __global__ void __launch_bounds__(128) fb_sweeps_kernel(Plan pl, Workspace ws, R
             rho2 = rho3;
         };
         Vec<SPL> bufA[PF], bufB[PF];
-        // slot i of a burst starting at step i0 holds the row of frame T-2-(i0+i)
-        auto bchunk = [&](const int i0, Vec<SPL>(&cur)[PF], Vec<SPL>(&nxt)[PF], const bool check) {
+        float cbA[NC], cbB[NC];
+        // slot i of a burst starting at step i0 holds the row (and c) of frame T-2-(i0+i)
+        auto bchunk = [&](const int i0, Vec<SPL>(&cur)[PF], Vec<SPL>(&nxt)[PF], const float (&cc)[NC], float (&nc)[NC], const bool check) {
 #pragma unroll
             for (int i = 0; i < PF; ++i) nxt[i] = ldo<SPL>(pp + (int64_t)max(T - 2 - (i0 + PF + i), 0) * S_PAD);
 #pragma unroll
-            for (int i = 0; i < PF; ++i) bstep(i0 + i, cur[i], check);
+            for (int k = 0; k < NC; ++k) nc[k] = ldo<1>(cv + max(T - 2 - (i0 + PF + k * LPR + l), 0)).v[0];
+#pragma unroll
+            for (int i = 0; i < PF; ++i) bstep(i0 + i, cur[i], shfl_pin(cc[i / LPR], gl0 + i % LPR), check);
         };
 #pragma unroll
         for (int i = 0; i < PF; ++i) bufA[i] = ldg_vec<SPL>(pp + (int64_t)max(T - 2 - i, 0) * S_PAD);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) cbA[k] = __ldg(cv + max(T - 2 - (k * LPR + l), 0));
         int i0 = 0;
         for (; i0 + 2 * PF <= Tmin - 1; i0 += 2 * PF) {
-            bchunk(i0, bufA, bufB, false);
-            bchunk(i0 + PF, bufB, bufA, false);
+            bchunk(i0, bufA, bufB, cbA, cbB, false);
+            bchunk(i0 + PF, bufB, bufA, cbB, cbA, false);
         }
         for (; i0 < Tmax - 1; i0 += 2 * PF) {
-            bchunk(i0, bufA, bufB, true);
-            bchunk(i0 + PF, bufB, bufA, true);
+            bchunk(i0, bufA, bufB, cbA, cbB, true);
+            bchunk(i0 + PF, bufB, bufA, cbB, cbA, true);
         }
     }
 }

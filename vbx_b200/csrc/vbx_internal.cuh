@@ -47,6 +47,8 @@ struct Workspace {
     float *p = nullptr;        // [N,S]  exp(ll - rowmax)
     float *rowmax = nullptr;   // [N]
     float *rsigma = nullptr;   // [N]    1 / forward scale
+    float *cvec = nullptr;     // [N]    c_t = sum_j p[t,j] w_j, w = (1-loopP) pi + 1e-8: the one reduction of the look-ahead
+                               //        sweeps that does not depend on the recursion, taken out of them (written by loglik)
     float *partial = nullptr;  // [n_mtiles,S,R] per-tile gamma^T rho
     float *A = nullptr;        // [n_rec,S,R]  Fa * alpha
     float *Afrag_hi = nullptr; // [n_rec,NT,KS,32] float2: Fa*alpha split to TF32 hi/lo, mma fragment-major
@@ -180,7 +182,8 @@ int launch_mstep_partial(const Plan &pl, const Workspace &ws, const float *rho, 
 int launch_speaker_model(const Plan &pl, const Workspace &ws, const RunParams &rp, const float *Phi,
                          const int32_t *n_states, float *alpha_io, float *invL_io, bool from_given,
                          cudaStream_t st);
-int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st);
+int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, const float *pi, const int32_t *n_states, float loopP,
+                  cudaStream_t st);
 int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                             const int32_t *n_states, double *Li, int32_t *n_iters, int32_t *flags, int iter,
                             int spl, int classic, cudaStream_t st);
@@ -193,7 +196,8 @@ int launch_forward_backward_long(const Plan &pl, const Workspace &ws, const RunP
                                  const int32_t *n_states, cudaStream_t st);
 // tensor-core (mma.sync 3xTF32) versions of the two in-loop contractions (vbx_mma_kernels.cu)
 int launch_mstep_mma(const Plan &pl, const Workspace &ws, const float *rho, const float *gamma, cudaStream_t st);
-int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st);
+int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, const float *pi, const int32_t *n_states, float loopP,
+                      cudaStream_t st);
 // float64 finishing phase of vbx_run (vbx_exact64.cu)
 int launch_snapshot(const Plan &pl, const Workspace &ws, const float *gamma, const float *pi, int iter, cudaStream_t st);
 int launch_exact64_round(const Plan &pl, const Workspace &ws, const RunParams &rp, const float *rho, const float *Phi,

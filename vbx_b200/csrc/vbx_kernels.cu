@@ -521,7 +521,8 @@ int launch_speaker_model(const Plan &pl, const Workspace &ws, const RunParams &r
 // states and walks k in float4 steps.
 // ------------------------------------------------------------------------------------------------
 template <int S_PAD>
-__global__ void __launch_bounds__(128) loglik_kernel(Plan pl, Workspace ws, const float *__restrict__ rho) {
+__global__ void __launch_bounds__(128) loglik_kernel(Plan pl, Workspace ws, const float *__restrict__ rho,
+                                                     const float *__restrict__ pi, const int32_t *__restrict__ n_states, const float Q) {
     constexpr int SL = S_PAD < 8 ? S_PAD : 8;  // state lanes
     constexpr int SJ = S_PAD / SL;             // states per thread (strided by SL)
     constexpr int FL = 128 / SL;               // frame lanes
@@ -576,6 +577,15 @@ __global__ void __launch_bounds__(128) loglik_kernel(Plan pl, Workspace ws, cons
                 acc[i][j] = fmaf(x[i].w, a[j].w, acc[i][j]);
             }
     }
+    float wv[SJ];                    // transition weights w = Q pi + 1e-8 of this thread's states (VBx/VBx.py:98,159)
+    {
+        const int ns = n_states ? n_states[rec] : S_PAD;
+#pragma unroll
+        for (int j = 0; j < SJ; ++j) {
+            const int s = sl + SL * j;
+            wv[j] = s < ns ? fmaf(Q, pi[(int64_t)rec * S_PAD + s], VBX_EPS_TR) : 0.f;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < FJ; ++i) {
         float m = acc[i][0];
@@ -583,11 +593,21 @@ __global__ void __launch_bounds__(128) loglik_kernel(Plan pl, Workspace ws, cons
         for (int j = 1; j < SJ; ++j) m = fmaxf(m, acc[i][j]);
         m = group_max<SL>(m);
         const int fr = fl + FL * i;
+        float pv[SJ], c = 0.f;
+#pragma unroll
+        for (int j = 0; j < SJ; ++j) {
+            pv[j] = expf(acc[i][j] - m);
+            c = fmaf(pv[j], wv[j], c);
+        }
+        if (pl.split) c = group_sum<SL>(c);   // c_t = sum_j p[t,j] w_j, consumed by the split sweeps (CTA-uniform branch)
         if (fr < len) {
             float *dst = ws.p + (f0 + fr) * S_PAD + sl;
 #pragma unroll
-            for (int j = 0; j < SJ; ++j) dst[SL * j] = expf(acc[i][j] - m);
-            if (sl == 0) ws.rowmax[f0 + fr] = m;
+            for (int j = 0; j < SJ; ++j) dst[SL * j] = pv[j];
+            if (sl == 0) {
+                ws.rowmax[f0 + fr] = m;
+                if (pl.split) ws.cvec[f0 + fr] = c;
+            }
         }
     }
 }
@@ -595,7 +615,8 @@ __global__ void __launch_bounds__(128) loglik_kernel(Plan pl, Workspace ws, cons
 static size_t loglik_smem(int S_pad, int R) { return (size_t)(kLTile + S_pad) * (R + 4) * sizeof(float); }
 
 template <int S_PAD>
-static int launch_loglik_t(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st) {
+static int launch_loglik_t(const Plan &pl, const Workspace &ws, const float *rho, const float *pi, const int32_t *n_states, float loopP,
+                           cudaStream_t st) {
     const size_t smem = loglik_smem(S_PAD, pl.R);
     static bool configured = false;
     if (!configured) {
@@ -604,18 +625,19 @@ static int launch_loglik_t(const Plan &pl, const Workspace &ws, const float *rho
             return -1;
         configured = true;
     }
-    loglik_kernel<S_PAD><<<pl.n_ltiles, 128, smem, st>>>(pl, ws, rho);
+    loglik_kernel<S_PAD><<<pl.n_ltiles, 128, smem, st>>>(pl, ws, rho, pi, n_states, 1.f - loopP);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st) {
+int launch_loglik(const Plan &pl, const Workspace &ws, const float *rho, const float *pi, const int32_t *n_states, float loopP,
+                  cudaStream_t st) {
     if (pl.n_ltiles == 0) return 0;
     switch (pl.S) {
-        case 4: return launch_loglik_t<4>(pl, ws, rho, st);
-        case 8: return launch_loglik_t<8>(pl, ws, rho, st);
-        case 16: return launch_loglik_t<16>(pl, ws, rho, st);
-        case 32: return launch_loglik_t<32>(pl, ws, rho, st);
-        case 64: return launch_loglik_t<64>(pl, ws, rho, st);
+        case 4: return launch_loglik_t<4>(pl, ws, rho, pi, n_states, loopP, st);
+        case 8: return launch_loglik_t<8>(pl, ws, rho, pi, n_states, loopP, st);
+        case 16: return launch_loglik_t<16>(pl, ws, rho, pi, n_states, loopP, st);
+        case 32: return launch_loglik_t<32>(pl, ws, rho, pi, n_states, loopP, st);
+        case 64: return launch_loglik_t<64>(pl, ws, rho, pi, n_states, loopP, st);
         default: return -1;
     }
 }

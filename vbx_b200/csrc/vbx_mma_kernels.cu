@@ -207,9 +207,13 @@ int launch_mstep_mma(const Plan &pl, const Workspace &ws, const float *rho, cons
 // (ws.Afrag_hi/lo: [rec][n-tile][k-step][lane] float2), staged once per CTA in shared memory.
 // One CTA (4 warps) per <=256-frame tile, a warp owns every 4th 16-frame m-tile.
 // ------------------------------------------------------------------------------------------------
-template <int S_PAD, bool R128>
-__global__ void __launch_bounds__(128, 3) loglik_mma_kernel(Plan pl, Workspace ws,
-                                                                               const float *__restrict__ rho) {
+// WITH_C: also emit c_t = sum_j p[t,j] w_j (w = (1-loopP) pi + 1e-8), the reduction the split sweeps take out of their
+// recursion (vbx_fb_split.cu).  Costs ~14 % of this kernel's time on bandwidth-bound batches, so only plans that chose the
+// split sweeps (small batches) instantiate it.
+template <int S_PAD, bool R128, bool WITH_C>
+__global__ void __launch_bounds__(128, 3) loglik_mma_kernel(Plan pl, Workspace ws, const float *__restrict__ rho,
+                                                            const float *__restrict__ pi, const int32_t *__restrict__ n_states,
+                                                            const float Q) {
     constexpr int NT = S_PAD > 8 ? S_PAD / 8 : 1;
     extern __shared__ uint2 sfrag[];
     const int R = pl.R;
@@ -233,12 +237,15 @@ __global__ void __launch_bounds__(128, 3) loglik_mma_kernel(Plan pl, Workspace w
         }
         asm volatile("cp.async.commit_group;\n" ::);
     }
-    float nb[NT][2];
+    float nb[NT][2], wv[NT][2];      // -bias and the transition weights w = Q pi + 1e-8 of this thread's states
+    const int ns = n_states ? n_states[rec] : S_PAD;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
         const int s = 8 * i + 2 * q;
         nb[i][0] = s < S_PAD ? -ws.bias[(int64_t)rec * S_PAD + s] : -CUDART_INF_F;
         nb[i][1] = s + 1 < S_PAD ? -ws.bias[(int64_t)rec * S_PAD + s + 1] : -CUDART_INF_F;
+        wv[i][0] = (WITH_C && s < ns) ? fmaf(Q, pi[(int64_t)rec * S_PAD + s], VBX_EPS_TR) : 0.f;
+        wv[i][1] = (WITH_C && s + 1 < ns) ? fmaf(Q, pi[(int64_t)rec * S_PAD + s + 1], VBX_EPS_TR) : 0.f;
     }
     const int n_mt = (len + 15) >> 4;
 
@@ -258,19 +265,36 @@ __global__ void __launch_bounds__(128, 3) loglik_mma_kernel(Plan pl, Workspace w
         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
         const int ra = mt * 16 + g, rb = ra + 8;
+        float c0 = 0.f, c1 = 0.f;                  // c_t = sum_j p[t,j] w_j for the two rows
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
             const int s = 8 * i + 2 * q;
             if (s < S_PAD) {
-                if (ra < len)
-                    *reinterpret_cast<float2 *>(ws.p + (f0 + ra) * S_PAD + s) = make_float2(expf(D[i][0] - m0), expf(D[i][1] - m0));
-                if (rb < len)
-                    *reinterpret_cast<float2 *>(ws.p + (f0 + rb) * S_PAD + s) = make_float2(expf(D[i][2] - m1), expf(D[i][3] - m1));
+                const float2 pa = make_float2(expf(D[i][0] - m0), expf(D[i][1] - m0));
+                const float2 pb = make_float2(expf(D[i][2] - m1), expf(D[i][3] - m1));
+                if (WITH_C) {
+                    c0 = fmaf(pa.x, wv[i][0], fmaf(pa.y, wv[i][1], c0));
+                    c1 = fmaf(pb.x, wv[i][0], fmaf(pb.y, wv[i][1], c1));
+                }
+                if (ra < len) *reinterpret_cast<float2 *>(ws.p + (f0 + ra) * S_PAD + s) = pa;
+                if (rb < len) *reinterpret_cast<float2 *>(ws.p + (f0 + rb) * S_PAD + s) = pb;
             }
         }
+        if (WITH_C) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
+            c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+        }
         if (q == 0) {
-            if (ra < len) ws.rowmax[f0 + ra] = m0;
-            if (rb < len) ws.rowmax[f0 + rb] = m1;
+            if (ra < len) {
+                ws.rowmax[f0 + ra] = m0;
+                if (WITH_C) ws.cvec[f0 + ra] = c0;
+            }
+            if (rb < len) {
+                ws.rowmax[f0 + rb] = m1;
+                if (WITH_C) ws.cvec[f0 + rb] = c1;
+            }
         }
     };
     // The split terms go to separate accumulators (E: lo*hi + hi*lo, D: hi*hi) so that consecutive mma of a k-step
@@ -374,32 +398,43 @@ static size_t loglik_mma_smem(int S_pad, int R) {
 }
 
 template <int S_PAD>
-static int launch_loglik_mma_t(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st) {
+static int launch_loglik_mma_t(const Plan &pl, const Workspace &ws, const float *rho, const float *pi, const int32_t *n_states,
+                               float loopP, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(loglik_mma_kernel<S_PAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)loglik_mma_smem(S_PAD, kMaxR)) != cudaSuccess ||
-            cudaFuncSetAttribute(loglik_mma_kernel<S_PAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)loglik_mma_smem(S_PAD, kMaxR)) != cudaSuccess)
+        const int big = (int)loglik_mma_smem(S_PAD, kMaxR);
+        if (cudaFuncSetAttribute(loglik_mma_kernel<S_PAD, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+            cudaFuncSetAttribute(loglik_mma_kernel<S_PAD, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+            cudaFuncSetAttribute(loglik_mma_kernel<S_PAD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+            cudaFuncSetAttribute(loglik_mma_kernel<S_PAD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess)
             return -1;
         configured = true;
     }
     const size_t smem = loglik_mma_smem(S_PAD, pl.R);
-    if (pl.R == 128)
-        loglik_mma_kernel<S_PAD, true><<<pl.n_mtiles, 128, smem, st>>>(pl, ws, rho);
-    else
-        loglik_mma_kernel<S_PAD, false><<<pl.n_mtiles, 128, smem, st>>>(pl, ws, rho);
+    const float Q = 1.f - loopP;
+    if (pl.split) {
+        if (pl.R == 128)
+            loglik_mma_kernel<S_PAD, true, true><<<pl.n_mtiles, 128, smem, st>>>(pl, ws, rho, pi, n_states, Q);
+        else
+            loglik_mma_kernel<S_PAD, false, true><<<pl.n_mtiles, 128, smem, st>>>(pl, ws, rho, pi, n_states, Q);
+    } else {
+        if (pl.R == 128)
+            loglik_mma_kernel<S_PAD, true, false><<<pl.n_mtiles, 128, smem, st>>>(pl, ws, rho, pi, n_states, Q);
+        else
+            loglik_mma_kernel<S_PAD, false, false><<<pl.n_mtiles, 128, smem, st>>>(pl, ws, rho, pi, n_states, Q);
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, cudaStream_t st) {
+int launch_loglik_mma(const Plan &pl, const Workspace &ws, const float *rho, const float *pi, const int32_t *n_states, float loopP,
+                      cudaStream_t st) {
     if (pl.n_mtiles == 0) return 0;
     switch (pl.S) {
-        case 4: return launch_loglik_mma_t<4>(pl, ws, rho, st);
-        case 8: return launch_loglik_mma_t<8>(pl, ws, rho, st);
-        case 16: return launch_loglik_mma_t<16>(pl, ws, rho, st);
-        case 32: return launch_loglik_mma_t<32>(pl, ws, rho, st);
-        case 64: return launch_loglik_mma_t<64>(pl, ws, rho, st);
+        case 4: return launch_loglik_mma_t<4>(pl, ws, rho, pi, n_states, loopP, st);
+        case 8: return launch_loglik_mma_t<8>(pl, ws, rho, pi, n_states, loopP, st);
+        case 16: return launch_loglik_mma_t<16>(pl, ws, rho, pi, n_states, loopP, st);
+        case 32: return launch_loglik_mma_t<32>(pl, ws, rho, pi, n_states, loopP, st);
+        case 64: return launch_loglik_mma_t<64>(pl, ws, rho, pi, n_states, loopP, st);
         default: return -1;
     }
 }
