@@ -67,6 +67,9 @@ const char *vbx_last_error(vbx_handle_t h);
  * recording concurrently on separate warps followed by a combine pass (the choice for batches too small to fill the GPU;
  * results differ from the fused sweep by float32 rounding only, so pin it to 1 or 2 where bit-identical results for a
  * recording alone / inside a large batch matter).
+ * "fb_priority": 0 = auto (large batches), 1 = always, 2 = never launch the forward-backward sweep on a high-priority side
+ * stream of the handle (ordered against `stream` with events, still no host synchronisation), so that it interleaves with
+ * the bandwidth-bound kernels of ANOTHER handle working on the same device (vbx_b200/parts.py runs two halves of a batch).
  * Tuning knobs: "fb_states_per_lane" (0 = auto, 1, 2, 4), "fb_classic" (forward-backward sweep: 0 = one-step
  * look-ahead recurrences, 1 = normalise-every-frame), "projection" (0 = auto, 1 = FFMA tiles,
  * 2 = tcgen05 3xTF32), "gemm" (in-loop contractions: 0 = tensor cores in split-precision 3xTF32, 1 = FFMA),

@@ -25,12 +25,23 @@ struct vbx_handle_s {
     int opt_projection = 0;
     int opt_timing = 0;
     int opt_gemm = 0;  // 0 = mma.sync 3xTF32, 1 = FFMA
+    int opt_fold_speaker = 0;    // 1 = speaker model inside the tensor-core M-step kernel (last CTA of a recording).  Measured on
+                                 // the headline batch: M-step 0.414 -> 0.646 ms against 0.086 ms for the separate kernel (the
+                                 // 128-thread tails hold SM slots through S dependent L2 round trips), so it is off by default
     int opt_debug_sync = 0;      // 1 = synchronise after every launch group and name it on stderr (debugging aid)
     int opt_fb_split = 0;        // 0 = auto (few recordings: sweeps on separate warps), 1 = always, 2 = never
     int opt_exact_stop = 1;      // 1 = finish recordings in float64 once the ELBO step nears epsilon (vbx_exact64.cu)
     int opt_noise_c = 2;         // float32 noise bound of an ELBO difference = noise_c * 2^-24 * |ELBO|
     int opt_guard_mult = 16;     // a recording switches when its ELBO step < epsilon + guard_mult * noise bound
     int64_t launches = 0;
+    // The forward-backward sweep of a large batch is latency bound (a tenth of the warps an SM can hold).  When two
+    // sub-batches run on two streams (vbx_b200/parts.py) it should interleave with the other sub-batch's bandwidth-bound
+    // contractions, but the block scheduler hands out the CTAs of the grid that was launched first until none are left.
+    // The sweep therefore runs on a high-priority side stream of this handle (ordered against `stream` by two events):
+    // its CTAs take the next free SM slots ahead of the queued contraction CTAs of the other sub-batch.
+    int opt_fb_priority = 0;     // 0 = auto (large batches on the fused sweep), 1 = always, 2 = never
+    cudaStream_t hi_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // NCCL communicator owned by the caller (vbx_attach_comm); ncclAllReduce is resolved from the libnccl the process
     // already uses, so the library has no link-time dependency on NCCL
     void *nccl_comm = nullptr;
@@ -113,6 +124,7 @@ size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
     w.gpart = c.take<double>((size_t)pl.n_mtiles);
     w.prev_elbo = c.take<double>(B);
     w.active = c.take<int32_t>(B);
+    w.tile_done = c.take<int32_t>(B);
     w.scratch = c.take<float>(2 * vbx::kMaxS);
     if (pl.R == 128) w.tc_scratch = c.take<float>(vbx::tc_scratch_floats());
     if (pl.split) {
@@ -177,6 +189,19 @@ int vbx_create(int32_t device, vbx_handle_t *out) {
     if (prop.major != 10) return VBX_ERR_NO_DEVICE;  // kernels are built for sm_100a only
     vbx_handle_t h = new vbx_handle_s();
     h->device = device;
+    {
+        DeviceGuard guard(device);
+        int lo = 0, hi = 0;
+        if (guard.err != cudaSuccess || cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
+            if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+            delete h;
+            return VBX_ERR_CUDA;
+        }
+    }
     *out = h;
     return VBX_OK;
 }
@@ -185,6 +210,9 @@ int vbx_destroy(vbx_handle_t h) {
     if (!h) return VBX_ERR_ARG;
     DeviceGuard guard(h->device);
     if (h->plan_mem) cudaFree(h->plan_mem);
+    if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return VBX_OK;
@@ -206,6 +234,15 @@ int vbx_set_option(vbx_handle_t h, const char *name, int32_t value) {
     if (!strcmp(name, "gemm")) {
         if (value != 0 && value != 1) return fail(h, VBX_ERR_ARG, "gemm must be 0 (mma 3xTF32) or 1 (FFMA)");
         h->opt_gemm = value;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "fb_priority")) {
+        if (value < 0 || value > 2) return fail(h, VBX_ERR_ARG, "fb_priority must be 0 (auto), 1 (always) or 2 (never)");
+        h->opt_fb_priority = value;
+        return VBX_OK;
+    }
+    if (!strcmp(name, "fold_speaker")) {
+        h->opt_fold_speaker = value ? 1 : 0;
         return VBX_OK;
     }
     if (!strcmp(name, "debug_sync")) {
@@ -564,6 +601,7 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
     // With the float64 finishing phase a recording that switched lags one round behind (it redoes two iterations):
     // one extra round, in which only the float64 kernels run.
     const int rounds = max_iters + (rp.hybrid ? 1 : 0);
+    const bool fb_hi = h->opt_fb_priority == 1 || (h->opt_fb_priority == 0 && !pl.split && pl.n_rec >= 1024);
     for (int it = 0; it < rounds; ++it) {
         Range nvtx_iter("vbx_em_iteration");
         const bool given = it == 0 && warm_start;
@@ -573,12 +611,15 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
                 rc = counted(h, vbx::launch_snapshot(pl, h->ws, gamma_io, pi_io, it, st), "snapshot");
                 if (rc) return rc;
             }
+            // tensor-core M-step: the CTA finishing a recording's last tile also computes its speaker model (no extra launch)
+            const bool fold = !given && !h->opt_gemm && h->opt_fold_speaker;
             if (!given) {
                 Timed t(h, st, VBX_K_MSTEP);
-                rc = counted(h, h->opt_gemm ? vbx::launch_mstep_partial(pl, h->ws, rho, gamma_io, st) : vbx::launch_mstep_mma(pl, h->ws, rho, gamma_io, st), "mstep_partial");
+                rc = counted(h, h->opt_gemm ? vbx::launch_mstep_partial(pl, h->ws, rho, gamma_io, st)
+                                            : vbx::launch_mstep_mma(pl, h->ws, rho, gamma_io, fold, rp, Phi, n_states, alpha_io, invL_io, st), "mstep_partial");
             }
             if (rc) return rc;
-            {
+            if (!fold) {
                 Timed t(h, st, VBX_K_SPEAKER_MODEL);
                 rc = counted(h, vbx::launch_speaker_model(pl, h->ws, rp, Phi, n_states, alpha_io, invL_io, given, st), "speaker_model");
             }
@@ -588,9 +629,18 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
                 rc = counted(h, h->opt_gemm ? vbx::launch_loglik(pl, h->ws, rho, pi_io, n_states, rp.loopP, st) : vbx::launch_loglik_mma(pl, h->ws, rho, pi_io, n_states, rp.loopP, st), "loglik");
             }
             if (rc) return rc;
+            if (fb_hi) {   // the sweep on the high-priority side stream, ordered after the log-likelihoods and before the next M-step
+                cudaEventRecord(h->ev_fork, st);
+                cudaStreamWaitEvent(h->hi_stream, h->ev_fork, 0);
+            }
             {
-                Timed t(h, st, VBX_K_FWDBWD);
-                rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, h->opt_fb_classic, st), "forward_backward");
+                cudaStream_t fs = fb_hi ? h->hi_stream : st;
+                Timed t(h, fs, VBX_K_FWDBWD);
+                rc = counted(h, vbx::launch_forward_backward(pl, h->ws, rp, gamma_io, pi_io, n_states, Li_out, n_iters_out, flags_out, it, h->opt_fb_spl, h->opt_fb_classic, fs), "forward_backward");
+            }
+            if (fb_hi) {
+                cudaEventRecord(h->ev_join, h->hi_stream);
+                cudaStreamWaitEvent(st, h->ev_join, 0);
             }
             if (rc) return rc;
         }

@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(128) run_init_kernel(Plan pl, Workspace ws, co
     const bool ok = T > 0 && ns > 0;
     if (tid == 0) {
         ws.active[rec] = ok ? 1 : 0;
+        ws.tile_done[rec] = 0;
         if (ws.active64) {
             ws.active64[rec] = 0;
             ws.fresh[rec] = 0;
