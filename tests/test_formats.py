@@ -119,3 +119,27 @@ def test_shipped_model_files_when_present():
     np.testing.assert_array_equal(lda, m['lda'])
     mu, tr, psi = formats.read_kaldi_plda(os.path.join(ref_dir, 'plda'))
     np.testing.assert_array_equal(mu, m['plda_mu'])
+
+
+def test_text_plda_round_trip_and_ark_writer(tmp_path):
+    """Text-format Kaldi PLDA (VBx/kaldi_utils.py:41-48) and the ark writer used to build CLI fixtures."""
+    from vbx_b200 import formats
+    rng = np.random.default_rng(3)
+    mean, tr, psi = rng.standard_normal(6), rng.standard_normal((6, 6)), np.sort(rng.uniform(0.1, 5, 6))[::-1].copy()
+    f = str(tmp_path / 'plda.txt')
+    formats.write_kaldi_plda_text(f, mean, tr, psi)
+    m2, t2, p2 = formats.read_kaldi_plda(f)
+    assert np.array_equal(mean, m2) and np.array_equal(tr, t2) and np.array_equal(psi, p2)
+    assert open(f).read().startswith('<Plda>  [ ')
+    with pytest.raises(ValueError):
+        (tmp_path / 'bad.txt').write_text('<Nnet> [ 1 2 ]')
+        formats.read_kaldi_plda(str(tmp_path / 'bad.txt'))
+    keys = ['recA_0000-00000000-00000144', 'recA_0001-00000024-00000168', 'recB_0000-00000000-00000144']
+    X = rng.standard_normal((3, 8)).astype(np.float32)
+    ark = str(tmp_path / 'x.ark')
+    formats.write_vec_flt_ark(ark, keys, X)
+    got = formats.read_xvectors_by_recording(ark)
+    assert list(got) == ['recA', 'recB'] and got['recA'][0] == keys[:2] and np.array_equal(got['recA'][1], X[:2])
+    np.savez(str(tmp_path / 't.npz'), mean1=np.arange(4.0), mean2=np.arange(2.0), lda=np.ones((4, 2)))
+    m1, m2_, lda = formats.read_xvec_transform(str(tmp_path / 't.npz'))
+    assert m1.shape == (4,) and m2_.shape == (2,) and lda.shape == (4, 2)

@@ -144,3 +144,38 @@ def test_es2005a_everything_on_the_device(es, chain):
     assert np.array_equal(labels, es['labels'])
     assert np.abs(g.double().cpu().numpy() - es['gamma']).max() <= 5e-3
     assert len(lines) == 50
+
+
+@pytest.mark.gpu
+def test_command_line_batch_of_recordings_to_rttm(tmp_path):
+    """`python -m vbx_b200.cli` with the options of VBx/vbhmm.py on an archive holding TWO recordings (ES2005a twice under
+    different names): Kaldi ark + segments + text PLDA + transform in, one RTTM per recording out, equal to the reference's
+    exp/ES2005a.rttm up to speaker renaming."""
+    from vbx_b200 import cli, formats
+    z = np.load(os.path.join(GOLD, 'es2005a.npz'))
+    m = np.load(os.path.join(GOLD, 'es2005a_model.npz'))
+    T = z['x_raw'].shape[0]
+    keys, seg_lines = [], []
+    for rec in ('ES2005a', 'COPY0001'):
+        for i, (s, e) in enumerate(z['seg_times']):
+            k = f'{rec}_{i:04d}-{int(round(s * 100)):08d}-{int(round(e * 100)):08d}'
+            keys.append(k)
+            seg_lines.append(f'{k} {rec} {s!r} {e!r}')
+    formats.write_vec_flt_ark(str(tmp_path / 'x.ark'), keys, np.concatenate([z['x_raw'], z['x_raw']]))
+    (tmp_path / 'x.seg').write_text('\n'.join(seg_lines) + '\n')
+    formats.write_kaldi_plda_text(str(tmp_path / 'plda.txt'), m['plda_mu'], m['plda_tr'], m['plda_psi'])
+    np.savez(str(tmp_path / 'transform.npz'), mean1=m['mean1'], mean2=m['mean2'], lda=m['lda'])
+    rc = cli.main(['--init', 'AHC+VB', '--out-rttm-dir', str(tmp_path / 'out'), '--xvec-ark-file', str(tmp_path / 'x.ark'),
+                   '--segments-file', str(tmp_path / 'x.seg'), '--xvec-transform', str(tmp_path / 'transform.npz'),
+                   '--plda-file', str(tmp_path / 'plda.txt'), '--threshold', '-0.015', '--lda-dim', '128', '--Fa', '0.3',
+                   '--Fb', '17', '--loopP', '0.99', '--output-2nd', 'True'])
+    assert rc == 0
+    for rec in ('ES2005a', 'COPY0001'):
+        got = formats.read_rttm(str(tmp_path / 'out' / f'{rec}.rttm'))
+        assert len(got) == len(z['rttm_starts'])
+        mapping = {}
+        for (r, s, d, lab), s2, e2, l2 in zip(got, z['rttm_starts'], z['rttm_ends'], z['rttm_labels']):
+            assert r == rec and abs(s - s2) < 1e-5 and abs(d - (e2 - s2)) < 1e-5
+            assert mapping.setdefault(lab, int(l2)) == int(l2)
+        assert len(set(mapping.values())) == len(mapping)
+        assert os.path.exists(str(tmp_path / 'out2nd' / f'{rec}.rttm'))

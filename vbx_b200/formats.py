@@ -39,6 +39,14 @@ def read_vec_flt_ark(path):
         yield key, vec
 
 
+def write_vec_flt_ark(path, keys, vectors):
+    """Kaldi binary float-vector archive (what VBx/predict.py:193 writes): one float32 vector per key."""
+    with open(path, 'wb') as f:
+        for key, v in zip(keys, vectors):
+            v = np.ascontiguousarray(v, dtype='<f4')
+            f.write(key.encode('ascii') + b' ' + b'\0B' + b'FV ' + b'\x04' + struct.pack('<i', v.shape[0]) + v.tobytes())
+
+
 def read_xvectors_by_recording(path):
     """Group an ark by recording id = key up to the last '_' (VBx/vbhmm.py:119).
     Returns {recording: (list_of_keys, float array T x D)} preserving archive order."""
@@ -98,17 +106,52 @@ def _kaldi_mat(buf, pos):
     return m.reshape(rows, cols), pos + rows * cols * dt.itemsize
 
 
+def _text_tokens(txt, pos):
+    """Tokens of a Kaldi text object starting at `pos` up to and including its closing ']' -> (floats, next pos)."""
+    end = txt.index(']', pos)
+    body = txt[pos:end].replace('[', ' ')
+    return [float(t) for t in body.split()], end + 1
+
+
 def read_kaldi_plda(path):
-    """Binary Kaldi PLDA -> (mean, transform, psi) float64 (VBx/kaldi_utils.py:25-53)."""
+    """Kaldi PLDA, binary or text -> (mean, transform, psi) float64 (VBx/kaldi_utils.py:25-53).
+    Binary: '\\0B<Plda> ' vector matrix vector '</Plda> '.  Text: '<Plda>  [ mean ]\\n [\\n rows ]\\n [ psi ]\\n</Plda> '
+    (what `ivector-copy-plda --binary=false` writes; one matrix row per line)."""
     with open(path, 'rb') as f:
         buf = f.read()
-    pos = _kaldi_token(buf, 0, b'\0B')
-    pos = _kaldi_token(buf, pos, b'<Plda> ')
-    mean, pos = _kaldi_vec(buf, pos)
-    tr, pos = _kaldi_mat(buf, pos)
-    psi, pos = _kaldi_vec(buf, pos)
-    _kaldi_token(buf, pos, b'</Plda> ')
+    if buf[:2] == b'\0B':
+        pos = _kaldi_token(buf, 2, b'<Plda> ')
+        mean, pos = _kaldi_vec(buf, pos)
+        tr, pos = _kaldi_mat(buf, pos)
+        psi, pos = _kaldi_vec(buf, pos)
+        _kaldi_token(buf, pos, b'</Plda> ')
+        return mean, tr, psi
+    txt = buf.decode('ascii')
+    if not txt.lstrip().startswith('<Plda>'):
+        raise ValueError(f'{path}: not a Kaldi PLDA model')
+    pos = txt.index('<Plda>') + len('<Plda>')
+    mean, pos = _text_tokens(txt, pos)
+    # the matrix: rows are separated by newlines inside one bracket pair
+    lb = txt.index('[', pos)
+    rb = txt.index(']', lb)
+    rows = [line.split() for line in txt[lb + 1:rb].strip().splitlines() if line.strip()]
+    tr = np.array([[float(v) for v in r] for r in rows], dtype=np.float64)
+    psi, pos = _text_tokens(txt, rb + 1)
+    if '</Plda>' not in txt[pos:]:
+        raise ValueError(f'{path}: missing </Plda>')
+    mean, psi = np.array(mean, dtype=np.float64), np.array(psi, dtype=np.float64)
+    if tr.ndim != 2 or tr.shape[0] != tr.shape[1] or tr.shape[0] != mean.shape[0] or psi.shape[0] != mean.shape[0]:
+        raise ValueError(f'{path}: inconsistent PLDA dimensions {mean.shape} {tr.shape} {psi.shape}')
     return mean, tr, psi
+
+
+def write_kaldi_plda_text(path, mean, tr, psi):
+    """Text form of a Kaldi PLDA (fixtures / interchange)."""
+    with open(path, 'w') as f:
+        f.write('<Plda>  [ ' + ' '.join(repr(float(v)) for v in mean) + ' ]\n [\n')
+        for i, row in enumerate(tr):
+            f.write('  ' + ' '.join(repr(float(v)) for v in row) + (' ]\n' if i == len(tr) - 1 else '\n'))
+        f.write(' [ ' + ' '.join(repr(float(v)) for v in psi) + ' ]\n</Plda> ')
 
 
 def read_xvec_transform(path):
@@ -116,6 +159,10 @@ def read_xvec_transform(path):
     read through h5py at VBx/vbhmm.py:125-128).  Both shipped models use an HDF5 v0 superblock with
     contiguous datasets at fixed offsets; this reader validates the signature / size / dataset names
     and slices them out (a general HDF5 parser is out of scope)."""
+    if str(path).endswith('.npz'):          # the same three arrays without HDF5 (np.savez(path, mean1=, mean2=, lda=))
+        z = np.load(path)
+        return (np.asarray(z['mean1'], dtype=np.float64), np.asarray(z['mean2'], dtype=np.float64),
+                np.asarray(z['lda'], dtype=np.float64))
     with open(path, 'rb') as f:
         buf = f.read()
     if buf[:8] != b'\x89HDF\r\n\x1a\n' or len(buf) != 267264:

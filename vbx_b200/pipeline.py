@@ -132,3 +132,90 @@ def diarize_recording(x_raw, seg_times, ahc_labels, transform, plda, Fa, Fb, loo
     s, e, l = merge_adjacent_labels(seg_times[:, 0], seg_times[:, 1], labels)
     vb.close()
     return rttm_lines(recording, s, e, l), labels, g[:, :S]
+
+
+def diarize_batch(recordings, transform, plda, Fa, Fb, loopP, lda_dim=128, threshold=-0.015, smoothing=5.0, init='AHC+VB',
+                  max_iters=40, epsilon=1e-6, device=None, chain='auto', output_2nd=False):
+    """Every recording of an archive in ONE batch on the device - the body of the loop VBx/vbhmm.py:120-179 for all
+    recordings at once: x-vector transform + PLDA projection (vbx_prepare_xvectors), AHC initialisation (vbx_ahc), the
+    VB-HMM with the reference's stop rule (vbx_run), hard labels (vbx_hard_labels); merging and RTTM lines on the host.
+
+    recordings: {name: (x_raw [T,Dx] float array, seg_times [T,2])} in archive order.  transform = (mean1, mean2, lda),
+    plda = (mu, tr, psi) as read from the Kaldi model (diagonalised here as VBx/vbhmm.py:107-113 does).
+    init: 'AHC' (clustering only) or 'AHC+VB' (VBx/vbhmm.py:131,147).  chain: 'tcgen05' (fused tensor-core front end,
+    needs lda_dim == 128 and a 128-dim PLDA), 'float64' (float64 torch ops), 'auto' = tcgen05 when the shapes allow.
+    Returns {name: dict(rttm, labels, labels2nd or None, n_speakers, iterations)}."""
+    from .batch import VbxBatch
+    from . import ahc as _ahc
+    if init not in ('AHC', 'AHC+VB'):
+        raise ValueError('Wrong option for args.initialization.')          # VBx/vbhmm.py:163-164
+    if not torch.cuda.is_available():
+        from ._lib import VbxError
+        raise VbxError('diarize_batch(): no CUDA device - vbx_b200 has no CPU fallback')
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    names = list(recordings)
+    lens = np.array([np.asarray(recordings[n][0]).shape[0] for n in names], dtype=np.int64)
+    if len(names) == 0:
+        return {}
+    f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    f32 = lambda a: f64(a).float().contiguous()
+    mu, tr, psi = diagonalise_plda(*plda)
+    mean1, mean2, lda = transform
+    Dx = int(np.asarray(recordings[names[0]][0]).shape[1])
+    if chain == 'auto':
+        chain = 'tcgen05' if (lda_dim == 128 and tr.shape[0] == 128 and lda.shape[1] == 128 and Dx % 32 == 0) else 'float64'
+    x_all = np.concatenate([np.asarray(recordings[n][0], dtype=np.float64) for n in names])
+    front = VbxBatch(lens, 128 if chain == 'tcgen05' else 4, 1, device=dev, exact_stop=False)
+    if chain == 'tcgen05':
+        rho, x = front.prepare_xvectors(f32(x_all), f32(mean1), f32(lda), f32(mean2), f32(mu), f32(tr), f32(psi))
+        Phi = f32(psi)
+        fea = (rho / torch.sqrt(Phi)[None, :]).contiguous()
+    else:
+        x = xvector_transform(f64(x_all), f64(mean1), f64(mean2), f64(lda)).contiguous()
+        fea = plda_project(x, f64(mu), f64(tr), lda_dim).float().contiguous()
+        Phi = f64(psi[:lda_dim]).float().contiguous()
+    ahc_labels, _, _ = _ahc.ahc_batch(front, x, threshold=threshold)      # VBx/vbhmm.py:131-146
+    front.close()
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    out = {}
+    labels1 = [l.astype(np.int64) for l in ahc_labels]
+    labels2 = [None] * len(names)
+    iters = [0] * len(names)
+    if init.endswith('VB'):
+        ns = np.array([int(l.max()) + 1 if len(l) else 1 for l in ahc_labels], dtype=np.int32)
+        if ns.max() > 64:
+            bad = names[int(ns.argmax())]
+            raise ValueError(f'recording {bad!r}: AHC produced {int(ns.max())} clusters; the VB-HMM kernels hold at most 64 HMM states '
+                             '(raise --threshold, or run that recording with --init AHC)')
+        R = int(fea.shape[1])
+        pad = (-R) % 4
+        if pad:                     # inert zero features (see api.VBx): labels do not depend on them
+            fea = torch.cat([fea, torch.zeros((fea.shape[0], pad), device=dev)], dim=1).contiguous()
+            Phi = torch.cat([Phi, torch.zeros(pad, device=dev)]).contiguous()
+        vb = VbxBatch(lens, R + pad, ns, device=dev)
+        lab_d = torch.from_numpy(np.concatenate(ahc_labels)).to(dev)
+        g = torch.zeros((int(lens.sum()), vb.S), dtype=torch.float32, device=dev)
+        p = torch.zeros((len(names), vb.S), dtype=torch.float32, device=dev)
+        for b in range(len(names)):              # VBx/vbhmm.py:150-152: qinit = softmax(onehot * smoothing)
+            g[offs[b]:offs[b + 1], :ns[b]] = soft_init(lab_d[offs[b]:offs[b + 1]], int(ns[b]), smoothing)
+            p[b, :ns[b]] = 1.0 / ns[b]
+        vb.prepare_scale(fea, Phi)
+        res = vb.run(g, p, Fa=Fa, Fb=Fb, loopProb=loopP, maxIters=max_iters, epsilon=epsilon)     # VBx/vbhmm.py:154-158
+        first, second = vb.hard_labels(g, second=True)                     # VBx/vbhmm.py:160-162
+        first, second = first.cpu().numpy().astype(np.int64), second.cpu().numpy().astype(np.int64)
+        iters = res['n_iters'].cpu().numpy().tolist()
+        for b in range(len(names)):
+            labels1[b] = first[offs[b]:offs[b + 1]]
+            if ns[b] > 1:
+                labels2[b] = second[offs[b]:offs[b + 1]]
+        vb.close()
+    for b, n in enumerate(names):
+        seg = np.asarray(recordings[n][1], dtype=np.float64)
+        s, e, l = merge_adjacent_labels(seg[:, 0], seg[:, 1], labels1[b])   # VBx/vbhmm.py:169
+        item = dict(rttm=rttm_lines(n, s, e, l), labels=labels1[b], labels2nd=labels2[b], iterations=int(iters[b]),
+                    n_speakers=int(len(set(labels1[b].tolist()))), rttm2nd=None)
+        if output_2nd and labels2[b] is not None:
+            s2, e2, l2 = merge_adjacent_labels(seg[:, 0], seg[:, 1], labels2[b])   # VBx/vbhmm.py:174-179
+            item['rttm2nd'] = rttm_lines(n, s2, e2, l2)
+        out[n] = item
+    return out
