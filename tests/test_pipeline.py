@@ -160,7 +160,7 @@ def test_command_line_batch_of_recordings_to_rttm(tmp_path):
         for i, (s, e) in enumerate(z['seg_times']):
             k = f'{rec}_{i:04d}-{int(round(s * 100)):08d}-{int(round(e * 100)):08d}'
             keys.append(k)
-            seg_lines.append(f'{k} {rec} {s!r} {e!r}')
+            seg_lines.append(f'{k} {rec} {float(s)!r} {float(e)!r}')
     formats.write_vec_flt_ark(str(tmp_path / 'x.ark'), keys, np.concatenate([z['x_raw'], z['x_raw']]))
     (tmp_path / 'x.seg').write_text('\n'.join(seg_lines) + '\n')
     formats.write_kaldi_plda_text(str(tmp_path / 'plda.txt'), m['plda_mu'], m['plda_tr'], m['plda_psi'])
