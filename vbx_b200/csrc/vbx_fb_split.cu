@@ -438,10 +438,9 @@ __global__ void __launch_bounds__(128) fb_split_tail_kernel(Plan pl, Workspace w
     }
 }
 
-template <int S_PAD>
+template <int S_PAD, int SPL>
 int launch_split_t(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi, const int32_t *n_states,
                    cudaStream_t st) {
-    constexpr int SPL = S_PAD >= 16 ? 2 : 1;
     constexpr int RPW = 32 / (S_PAD / SPL);
     constexpr int LPF = S_PAD / (S_PAD < 16 ? S_PAD : 16), FBK = 256 / LPF, LD = 2 * S_PAD + 1, NCOL = 2 * S_PAD, NPART = 256 / NCOL;
     const int n_warps = (pl.n_rec + RPW - 1) / RPW;
@@ -460,17 +459,30 @@ int launch_split_t(const Plan &pl, const Workspace &ws, const RunParams &rp, flo
 
 }  // namespace
 
+// spl: states per lane of the sweeps (0 = default: 2 from 16 states up, else 1)
 int launch_forward_backward_split(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
-                                  const int32_t *n_states, cudaStream_t st) {
+                                  const int32_t *n_states, int spl, cudaStream_t st) {
     if (pl.n_rec == 0 || pl.n_mtiles == 0) return 0;
+#define VBX_SP(S_, L_) return launch_split_t<S_, L_>(pl, ws, rp, gamma, pi, n_states, st)
     switch (pl.S) {
-        case 4: return launch_split_t<4>(pl, ws, rp, gamma, pi, n_states, st);
-        case 8: return launch_split_t<8>(pl, ws, rp, gamma, pi, n_states, st);
-        case 16: return launch_split_t<16>(pl, ws, rp, gamma, pi, n_states, st);
-        case 32: return launch_split_t<32>(pl, ws, rp, gamma, pi, n_states, st);
-        case 64: return launch_split_t<64>(pl, ws, rp, gamma, pi, n_states, st);
+        case 4: VBX_SP(4, 1);
+        case 8:
+            if (spl == 2) VBX_SP(8, 2);
+            VBX_SP(8, 1);
+        case 16:
+            if (spl == 1) VBX_SP(16, 1);
+            if (spl == 4) VBX_SP(16, 4);
+            VBX_SP(16, 2);
+        case 32:
+            if (spl == 1) VBX_SP(32, 1);
+            if (spl == 4) VBX_SP(32, 4);
+            VBX_SP(32, 2);
+        case 64:
+            if (spl == 4) VBX_SP(64, 4);
+            VBX_SP(64, 2);
         default: return -1;
     }
+#undef VBX_SP
 }
 
 }  // namespace vbx

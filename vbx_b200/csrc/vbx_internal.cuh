@@ -191,7 +191,7 @@ int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams
 int launch_elbo_trace(const Plan &pl, const double *Li, int max_iters, double *out, cudaStream_t st);
 // forward and backward sweeps on separate warps + combine pass, any recording length (vbx_fb_split.cu)
 int launch_forward_backward_split(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
-                                  const int32_t *n_states, cudaStream_t st);
+                                  const int32_t *n_states, int spl, cudaStream_t st);
 // chunked-scan forward-backward for long recordings (vbx_long_kernels.cu)
 int launch_forward_backward_long(const Plan &pl, const Workspace &ws, const RunParams &rp, float *gamma, float *pi,
                                  const int32_t *n_states, cudaStream_t st);

@@ -1351,7 +1351,7 @@ int launch_forward_backward(const Plan &pl, const Workspace &ws, const RunParams
                             int spl, int classic, cudaStream_t st) {
     if (pl.n_rec == 0) return 0;
     if (pl.split) {
-        const int rs = launch_forward_backward_split(pl, ws, rp, gamma, pi, n_states, st);
+        const int rs = launch_forward_backward_split(pl, ws, rp, gamma, pi, n_states, spl, st);
         if (rs < 0) return rs;
         elbo_kernel<<<pl.n_rec, 128, 0, st>>>(pl, ws, rp, Li, n_iters, flags, iter);
         return cudaGetLastError() == cudaSuccess ? rs + 1 : -1;
