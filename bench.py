@@ -650,6 +650,7 @@ def main():
             N_total = N
         timings = vb.timings(reset=True)
         launches = (vb.launches - l0) / steps
+        tr = trace.cpu().numpy()          # batch-wide ELBO trace of the last timed step (all ranks, in-library all-reduce)
         kernel_pass = 'in the timed region'
         if partitioned:
             gamma_keep, pi_keep, out_keep = gamma.clone(), pi.clone(), {k: v.clone() for k, v in out.items() if k in ('Li', 'n_iters')}
@@ -673,7 +674,6 @@ def main():
             out = dict(out, **out_keep)
             kernel_pass = ('separate serial pass of 3 steps (one stream); the step time itself has the two halves of the batch '
                            'overlapping on two streams, so these per-kernel times add up to more than ms_per_step')
-        tr = trace.cpu().numpy()
         assert np.all(np.isfinite(tr)), 'non-finite ELBO in the benchmark run'
         n_all = world * w['B'] if not strong else w['B']
         assert np.all(tr[w['iters']:] == n_all), (tr[w['iters']:], n_all)       # every recording of the job ran every iteration
