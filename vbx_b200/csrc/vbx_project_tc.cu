@@ -18,6 +18,12 @@
 //              128-byte lines per row.
 // Shared memory: 2 stages x (A hi/lo for 2 M-tiles 64 KB + B hi/lo 32 KB) = 192 KB.  TMEM: 2 accumulator sets of
 // 256 columns (all 512), so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// NS = 3 (the real-data front end): operands are split three ways, x = x1 + x2 + x3 exactly (3 x 11 mantissa bits), and
+// six products are accumulated (x3 v1, x1 v3, x2 v2, x2 v1, x1 v2, x1 v1): the dropped terms are below 2^-33, i.e. the
+// GEMM is at fp32-accumulate accuracy.  The shipped LDA matrix is badly conditioned (sum |a_k lda_kn| ~ 1e3 |sum|), so
+// the 2^-21 relative error per product of the two-way split is visible on real data.  Three images per operand fit the
+// same 192 KB with ONE M-tile (128 frames) per CTA tile: 2 stages x (A 48 KB + B 48 KB).
 #include <cuda.h>
 
 #include "vbx_internal.cuh"
@@ -26,11 +32,11 @@ namespace vbx {
 
 namespace {
 
-constexpr int kTileM = 256;                 // frames per CTA tile (two UMMA M=128 tiles)
+constexpr int kMaxTileM = 256;              // frames per CTA tile: two UMMA M=128 tiles (NS = 2) or one (NS = 3)
 constexpr int kKB = 32;                     // columns of X per pipeline block (= one 128-byte swizzle row)
 constexpr int kStages = 2;
 constexpr int kABytes = 128 * 128;          // one 128-row x 128-byte operand image
-constexpr int kStageBytes = 4 * kABytes + 2 * kABytes;  // A: 2 mtiles x hi/lo, B: hi/lo
+constexpr int kStageBytes = 4 * kABytes + 2 * kABytes;  // A: 2 mtiles x hi/lo, B: hi/lo  ==  A: 1 mtile x 3 parts, B: 3 parts
 constexpr int kProducerThreads = 256;
 constexpr int kEpiWarps = 8;                // two per TMEM lane quarter (one per M-tile)
 constexpr int kThreads = (9 + kEpiWarps) * 32;
@@ -126,18 +132,36 @@ __device__ __forceinline__ void split_rn(const float x, float &hi, float &lo) {
     lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
 }
 
-// ---- setup: V [D,128] -> per 32-row block of V the swizzled K-major images of V^T, hi and lo (16 KB each) ----
+// x = x1 + x2 + x3 exactly: 11 + 11 + <= 2 mantissa bits, each part a TF32 number
+__device__ __forceinline__ void split3_rn(const float x, float &x1, float &x2, float &x3) {
+    x1 = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    const float r1 = x - x1;                                   // exact
+    x2 = __uint_as_float((__float_as_uint(r1) + 0x1000u) & 0xffffe000u);
+    x3 = r1 - x2;                                              // exact, fits TF32
+}
+
+// ---- setup: V [D,128] -> per 32-row block of V the swizzled K-major images of V^T, NS parts of 16 KB each ----
+template <int NS>
 __global__ void build_v_images_kernel(const float *__restrict__ V, int D, float *__restrict__ img) {
     const int kb = blockIdx.x;                       // k-block
     for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) {
         const int n = i >> 5, kk = i & 31;           // row n of V^T, column kk inside the block
         const float v = V[(int64_t)(kb * kKB + kk) * 128 + n];
-        float hi, lo;
-        split_rn(v, hi, lo);
         const int c = kk >> 2, e = kk & 3;
         const int off = n * 32 + (((c ^ (n & 7)) << 2) | e);   // float index inside the 16 KB image
-        img[(int64_t)kb * 2 * 4096 + off] = hi;
-        img[(int64_t)kb * 2 * 4096 + 4096 + off] = lo;
+        float *dst = img + (int64_t)kb * NS * 4096 + off;
+        if (NS == 2) {
+            float hi, lo;
+            split_rn(v, hi, lo);
+            dst[0] = hi;
+            dst[4096] = lo;
+        } else {
+            float v1, v2, v3;
+            split3_rn(v, v1, v2, v3);
+            dst[0] = v1;
+            dst[4096] = v2;
+            dst[2 * 4096] = v3;
+        }
     }
 }
 
@@ -145,11 +169,15 @@ __global__ void build_v_images_kernel(const float *__restrict__ V, int D, float 
 // MODE 2  rho = (X - a_off) . V, G_t as above                                  (PLDA stage, VBx/vbhmm.py:153)
 // MODE 1  out = l2norm(l2norm(X - a_off) . V - e_off)                          (x-vector transform, VBx/vbhmm.py:125-129)
 //         the producers also accumulate ||x - a_off||^2 per row and hand it to the epilogue through shared memory
-template <int MODE>
+template <int MODE, int NS>
 __global__ void __launch_bounds__(kThreads, 1)
 project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vimg, float *__restrict__ rho, int64_t N,
                        int D, const float *__restrict__ Phi, float *__restrict__ gframe,
                        const float *__restrict__ a_off, const float *__restrict__ e_off) {
+    constexpr int MT = NS == 2 ? 2 : 1;          // UMMA M-tiles (128 frames) per CTA tile
+    constexpr int kTileM = 128 * MT;
+    constexpr int ROWS_PT = kTileM / 32;         // rows per producer thread
+    static_assert((MT * NS + NS) * kABytes == kStageBytes, "stage layout");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the stage buffers must be 1024-byte aligned (128-byte swizzle); the dynamic window starts at offset 0 of the
     // CTA's shared memory (no static __shared__ in this kernel), which is checked rather than padded for
@@ -158,7 +186,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
     float *s_inv_phi = reinterpret_cast<float *>(bars + 18);   // 128 floats: 1/Phi (MODE 0, 2) or e_off (MODE 1)
-    float *s_n1 = reinterpret_cast<float *>(smem + kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes);   // [2][256]
+    float *s_n1 = reinterpret_cast<float *>(smem + kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes);   // [2][kTileM]
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     // barrier ids
@@ -181,7 +209,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
-            mbar_init(tmem_empty(a), kEpiWarps * 32);
+            mbar_init(tmem_empty(a), 4 * MT * 32);     // the epilogue warps that own an M-tile
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -203,22 +231,22 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
         const int r0 = tid >> 3;          // rows r0 + 32 i, i = 0..7
         const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t n_blocks = my_tiles * n_kb;
-        float4 bufA[8], bufB[8];
-        float ss[8];                      // MODE 1: running ||x - a_off||^2 of this thread's 8 rows (its 4 columns)
+        float4 bufA[ROWS_PT], bufB[ROWS_PT];
+        float ss[ROWS_PT];                // MODE 1: running ||x - a_off||^2 of this thread's rows (its 4 columns)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss[i] = 0.f;
-        auto issue = [&](const int64_t b, float4(&buf)[8]) {
+        for (int i = 0; i < ROWS_PT; ++i) ss[i] = 0.f;
+        auto issue = [&](const int64_t b, float4(&buf)[ROWS_PT]) {
             if (b >= n_blocks) return;
             const int64_t tile = blockIdx.x + (b / n_kb) * gridDim.x;
             const int kb = (int)(b % n_kb);
             const int64_t row_base = tile * kTileM;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < ROWS_PT; ++i) {
                 const int64_t row = min(row_base + r0 + 32 * i, N - 1);
                 buf[i] = ldg_stream(reinterpret_cast<const float4 *>(X + row * D + kb * kKB) + c);
             }
         };
-        auto process = [&](const int64_t b, const float4(&buf)[8]) {
+        auto process = [&](const int64_t b, const float4(&buf)[ROWS_PT]) {
             const int s = (int)(b & 1);
             const uint32_t ph = (uint32_t)((b >> 1) & 1);
             const int kb = (int)(b % n_kb);
@@ -227,12 +255,12 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
             mbar_wait(empty(s), ph ^ 1);               // the MMAs that read this stage have completed
             const uint32_t stage = smem_base + s * kStageBytes;
             if (tid == 0) {
-                mbar_expect_tx(full_b(s), 2 * kABytes);
-                bulk_g2s(stage + 4 * kABytes, vimg + (int64_t)kb * 2 * 4096, 2 * kABytes, full_b(s));
+                mbar_expect_tx(full_b(s), NS * kABytes);
+                bulk_g2s(stage + MT * NS * kABytes, vimg + (int64_t)kb * NS * 4096, NS * kABytes, full_b(s));
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 32 * i;             // 0..255
+            for (int i = 0; i < ROWS_PT; ++i) {
+                const int r = r0 + 32 * i;             // 0..kTileM-1
                 const int mt = r >> 7, m = r & 127;
                 float4 hi, lo, x = buf[i];
                 if (MODE != 0) {
@@ -242,19 +270,30 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
                     x.w -= aoff.w;
                 }
                 if (MODE == 1) ss[i] = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ss[i]))));
-                split_rn(x.x, hi.x, lo.x);
-                split_rn(x.y, hi.y, lo.y);
-                split_rn(x.z, hi.z, lo.z);
-                split_rn(x.w, hi.w, lo.w);
                 const uint32_t off = (uint32_t)(m * 128 + ((c ^ (m & 7)) << 4));
-                st_shared_v4(stage + (mt * 2 + 0) * kABytes + off, hi);
-                st_shared_v4(stage + (mt * 2 + 1) * kABytes + off, lo);
+                if (NS == 2) {
+                    split_rn(x.x, hi.x, lo.x);
+                    split_rn(x.y, hi.y, lo.y);
+                    split_rn(x.z, hi.z, lo.z);
+                    split_rn(x.w, hi.w, lo.w);
+                    st_shared_v4(stage + (mt * 2 + 0) * kABytes + off, hi);
+                    st_shared_v4(stage + (mt * 2 + 1) * kABytes + off, lo);
+                } else {
+                    float4 lo2;
+                    split3_rn(x.x, hi.x, lo.x, lo2.x);
+                    split3_rn(x.y, hi.y, lo.y, lo2.y);
+                    split3_rn(x.z, hi.z, lo.z, lo2.z);
+                    split3_rn(x.w, hi.w, lo.w, lo2.w);
+                    st_shared_v4(stage + 0 * kABytes + off, hi);
+                    st_shared_v4(stage + 1 * kABytes + off, lo);
+                    st_shared_v4(stage + 2 * kABytes + off, lo2);
+                }
             }
             if (MODE == 1 && kb == n_kb - 1) {
                 // row norms of the finished tile: the 8 lanes that share a row are adjacent
                 float *dst = s_n1 + ((b / n_kb) & 1) * kTileM;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < ROWS_PT; ++i) {
                     float v = ss[i];
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -291,18 +330,27 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
                     tc_fence_after();
                     const uint32_t st_lo = desc_lo(smem_base + s * kStageBytes);   // descriptor word of the stage base
                     constexpr uint32_t kImg = kABytes >> 4;                        // one operand image, in 16-byte units
-                    const uint32_t b_hi = st_lo + 4 * kImg, b_lo = b_hi + kImg;
+                    const uint32_t b0 = st_lo + MT * NS * kImg;                    // B parts: b0, b0 + kImg, (b0 + 2 kImg)
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        const uint32_t a_hi = st_lo + (mt * 2 + 0) * kImg, a_lo = a_hi + kImg;
-                        const uint32_t d = tmem_base + (uint32_t)(acc * 256 + mt * 128);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t a0 = st_lo + mt * NS * kImg;                // A parts of this M-tile
+                        const uint32_t d = tmem_base + (uint32_t)(acc * (128 * MT) + mt * 128);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t koff = ks * 2;      // 8 tf32 = 32 bytes inside the swizzle row (16-byte units)
                             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                            umma_tf32(d, a_lo + koff, b_hi + koff, kDescHi, kIdesc, first);
-                            umma_tf32(d, a_hi + koff, b_lo + koff, kDescHi, kIdesc, 1u);
-                            umma_tf32(d, a_hi + koff, b_hi + koff, kDescHi, kIdesc, 1u);
+                            if (NS == 2) {                      // lo*hi + hi*lo + hi*hi
+                                umma_tf32(d, a0 + kImg + koff, b0 + koff, kDescHi, kIdesc, first);
+                                umma_tf32(d, a0 + koff, b0 + kImg + koff, kDescHi, kIdesc, 1u);
+                                umma_tf32(d, a0 + koff, b0 + koff, kDescHi, kIdesc, 1u);
+                            } else {                            // smallest terms first: x3 v1, x1 v3, x2 v2, x2 v1, x1 v2, x1 v1
+                                umma_tf32(d, a0 + 2 * kImg + koff, b0 + koff, kDescHi, kIdesc, first);
+                                umma_tf32(d, a0 + koff, b0 + 2 * kImg + koff, kDescHi, kIdesc, 1u);
+                                umma_tf32(d, a0 + kImg + koff, b0 + kImg + koff, kDescHi, kIdesc, 1u);
+                                umma_tf32(d, a0 + kImg + koff, b0 + koff, kDescHi, kIdesc, 1u);
+                                umma_tf32(d, a0 + koff, b0 + kImg + koff, kDescHi, kIdesc, 1u);
+                                umma_tf32(d, a0 + koff, b0 + koff, kDescHi, kIdesc, 1u);
+                            }
                         }
                     }
                     tc_commit(empty(s));                       // stage reusable once these MMAs retire
@@ -323,6 +371,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
         // ======================= epilogue =======================
         const int quarter = warp & 3;                  // TMEM lanes 32*quarter .. +31 are visible to this warp
         const int mt = (warp - 9) >> 2;                // M-tile handled by this warp
+        if (mt < MT) {                                 // with one M-tile per CTA tile the second group of four warps idles
         const uint32_t epi = smem_base + kStages * kStageBytes + 1024 + (warp - 9) * kEpiStageBytes;
         const uint32_t inv_phi_s = smem_u32(s_inv_phi);
         int acc = 0;
@@ -331,7 +380,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
             mbar_wait(tmem_full(acc), acc_ph);
             tc_fence_after();
             const int64_t row_base = tile * kTileM + mt * 128 + quarter * 32;
-            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + mt * 128);
+            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * (128 * MT) + mt * 128);
             // lane = row.  8 lanes then cover the 128 bytes of one row: every store instruction writes 4 full lines
             auto store_block = [&](const int cb) {
                 __syncwarp();
@@ -410,6 +459,7 @@ project_tcgen05_kernel(const float *__restrict__ X, const float *__restrict__ vi
                 acc_ph ^= 1;
             }
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -430,12 +480,12 @@ __global__ void build_plda_v_kernel(const float *__restrict__ tr, const float *_
 }
 
 // cudaFuncSetAttribute is per device; everything else the launches need comes from the caller's workspace
-bool g_configured[64][3] = {};
+bool g_configured[64][3][2] = {};
 
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes + 2 * kTileM * 4;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kEpiWarps * kEpiStageBytes + 2 * kMaxTileM * 4;
 
 // one GEMM pass [N,D] x [D,128] of the given MODE; V is row-major [D,128] in device memory
-template <int MODE>
+template <int MODE, int NS>
 int launch_gemm_tc(float *vimg, int64_t N, const float *X, int D, const float *V, const float *Phi, float *out, float *gframe,
                    const float *a_off, const float *e_off, cudaStream_t st, std::string *err) {
     int dev = 0;
@@ -444,20 +494,21 @@ int launch_gemm_tc(float *vimg, int64_t N, const float *X, int D, const float *V
         if (err) *err = "device index out of range";
         return -1;
     }
-    if (!g_configured[dev][MODE]) {
-        if (cudaFuncSetAttribute(project_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) !=
+    if (!g_configured[dev][MODE][NS - 2]) {
+        if (cudaFuncSetAttribute(project_tcgen05_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) !=
             cudaSuccess) {
             if (err) *err = "cudaFuncSetAttribute(smem) failed";
             return -1;
         }
-        g_configured[dev][MODE] = true;
+        g_configured[dev][MODE][NS - 2] = true;
     }
+    constexpr int kTileM = NS == 2 ? 256 : 128;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    build_v_images_kernel<<<D / kKB, 256, 0, st>>>(V, D, vimg);
+    build_v_images_kernel<NS><<<D / kKB, 256, 0, st>>>(V, D, vimg);
     const int64_t n_tiles = (N + kTileM - 1) / kTileM;
     const int grid = (int)std::min<int64_t>(n_tiles, sms);
-    project_tcgen05_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(X, vimg, out, N, D, Phi, gframe, a_off, e_off);
+    project_tcgen05_kernel<MODE, NS><<<grid, kThreads, kSmemBytes, st>>>(X, vimg, out, N, D, Phi, gframe, a_off, e_off);
     if (cudaGetLastError() != cudaSuccess) {
         if (err) *err = "tcgen05 projection launch failed";
         return -1;
@@ -469,7 +520,7 @@ int launch_gemm_tc(float *vimg, int64_t N, const float *X, int D, const float *V
 
 // Scratch of the tensor-core front end inside the caller's workspace: the swizzled hi/lo images of V (2 x 16 KB per
 // 32 rows of V) for D up to kTcMaxD, and the folded PLDA matrix of the x-vector chain.
-size_t tc_scratch_floats() { return (size_t)(kTcMaxD / kKB) * 2 * 4096 + 128 * 128; }
+size_t tc_scratch_floats() { return (size_t)(kTcMaxD / kKB) * 3 * 4096 + 128 * 128; }
 
 int launch_project_tcgen05(const Plan &pl, float *tc_scratch, const float *X, int D, const float *V, const float *Phi, float *rho,
                            float *gframe, cudaStream_t st, std::string *err) {
@@ -486,7 +537,7 @@ int launch_project_tcgen05(const Plan &pl, float *tc_scratch, const float *X, in
         return -1;
     }
     if (pl.n_frames == 0) return 0;
-    return launch_gemm_tc<0>(tc_scratch, pl.n_frames, X, D, V, Phi, rho, gframe, nullptr, nullptr, st, err);
+    return launch_gemm_tc<0, 2>(tc_scratch, pl.n_frames, X, D, V, Phi, rho, gframe, nullptr, nullptr, st, err);
 }
 
 // The caller-side chain of VBx/vbhmm.py:125-129,153 plus the scale of VBx/VBx.py:88-89 as two tensor-core passes:
@@ -508,11 +559,11 @@ int launch_xvector_chain_tcgen05(const Plan &pl, float *tc_scratch, const float 
         return -1;
     }
     if (pl.n_frames == 0) return 0;
-    float *v2 = tc_scratch + (size_t)(kTcMaxD / kKB) * 2 * 4096;
-    int n = launch_gemm_tc<1>(tc_scratch, pl.n_frames, x_raw, Dx, lda, nullptr, x_norm, nullptr, mean1, mean2, st, err);
+    float *v2 = tc_scratch + (size_t)(kTcMaxD / kKB) * 3 * 4096;
+    int n = launch_gemm_tc<1, 3>(tc_scratch, pl.n_frames, x_raw, Dx, lda, nullptr, x_norm, nullptr, mean1, mean2, st, err);
     if (n < 0) return -1;
     build_plda_v_kernel<<<64, 256, 0, st>>>(plda_tr, psi, v2);
-    int m = launch_gemm_tc<2>(tc_scratch, pl.n_frames, x_norm, 128, v2, psi, rho, gframe, plda_mu, nullptr, st, err);
+    int m = launch_gemm_tc<2, 3>(tc_scratch, pl.n_frames, x_norm, 128, v2, psi, rho, gframe, plda_mu, nullptr, st, err);
     if (m < 0) return -1;
     return n + m + 1;
 }
