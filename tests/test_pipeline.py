@@ -105,7 +105,8 @@ def test_es2005a_raw_xvectors_to_rttm_on_gpu(es):
                                       f32(m['plda_mu']), f32(m['plda_tr']), f32(m['plda_psi']))
     torch.cuda.synchronize()
     # The shipped LDA matrix is badly conditioned (sum |a_k lda_kn| ~ 1000 x |sum|), so float32-level arithmetic shows:
-    # numpy float32 reaches 3.9e-6 / 3.6e-5 on these two checks; split-precision TF32 carries 22 operand bits, 4x that.
+    # numpy float32 reaches 3.9e-6 / 3.6e-5 on these two checks.  The operands are split three ways (exact, 6 MMAs), so what
+    # is left is the float32 rounding of the model / inputs and the accumulation inside the tensor core (4x numpy's).
     e_x = np.abs(x_norm.double().cpu().numpy() - es['x_lda']).max()
     fea = rho.double().cpu().numpy() / np.sqrt(es['Phi'])[None, :]
     e_f = np.abs(fea - es['fea']).max()
@@ -121,7 +122,7 @@ def test_es2005a_raw_xvectors_to_rttm_on_gpu(es):
     assert np.array_equal(labels, es['labels'])
     e_g = np.abs(g.double().cpu().numpy() - es['gamma']).max()
     print('ES2005a chain: max |gamma - ref| = %.2e' % e_g)
-    assert e_g <= 5e-3
+    assert e_g <= 1e-4                       # the north-star bar, from raw x-vectors through both tensor-core passes
     assert len(lines) == 50 and all(l.startswith('SPEAKER ES2005a 1 ') for l in lines)
     starts = np.array([float(l.split()[3]) for l in lines])
     np.testing.assert_allclose(starts, es['rttm_starts'], atol=1e-3)
@@ -142,7 +143,7 @@ def test_es2005a_everything_on_the_device(es, chain):
         chain=chain, plda_is_diagonal=True, threshold=-0.015)
     assert g.shape[1] == es['gamma'].shape[1] == 31          # same AHC speaker count and numbering
     assert np.array_equal(labels, es['labels'])
-    assert np.abs(g.double().cpu().numpy() - es['gamma']).max() <= 5e-3
+    assert np.abs(g.double().cpu().numpy() - es['gamma']).max() <= 1e-4
     assert len(lines) == 50
 
 
