@@ -145,6 +145,17 @@ def read_kaldi_plda(path):
     return mean, tr, psi
 
 
+def write_kaldi_plda_binary(path, mean, tr, psi):
+    """Binary Kaldi PLDA with float64 payloads, the layout of the shipped models (VBx/kaldi_utils.py:37-49)."""
+    mean, tr, psi = (np.ascontiguousarray(a, dtype='<f8') for a in (mean, tr, psi))
+    with open(path, 'wb') as f:
+        f.write(b'\0B<Plda> ')
+        f.write(b'DV \x04' + struct.pack('<i', mean.shape[0]) + mean.tobytes())
+        f.write(b'DM \x04' + struct.pack('<i', tr.shape[0]) + b'\x04' + struct.pack('<i', tr.shape[1]) + tr.tobytes())
+        f.write(b'DV \x04' + struct.pack('<i', psi.shape[0]) + psi.tobytes())
+        f.write(b'</Plda> ')
+
+
 def write_kaldi_plda_text(path, mean, tr, psi):
     """Text form of a Kaldi PLDA (fixtures / interchange)."""
     with open(path, 'w') as f:
