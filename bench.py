@@ -162,7 +162,17 @@ class ClockSampler:
                     if val.lower().startswith('active'):
                         reasons.add(name)
         if not sm:   # region shorter than the sampling period: use every sample we have
-            sm = [float(l.split(',')[1]) for _, l in self.lines if len(l.split(',')) >= 9] or [float('nan')]
+            sm = [float(l.split(',')[1]) for _, l in self.lines if len(l.split(',')) >= 9]
+        if not sm:   # the sampling stream produced nothing: one direct query right after the region
+            try:
+                q = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                   capture_output=True, text=True, timeout=20).stdout.strip().split(',')
+                sm, smax = [float(q[1])], float(q[2])
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), q[5:9]):
+                    if val.strip().lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                sm = [float('nan')]
         return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
@@ -608,6 +618,10 @@ def main():
             trace.copy_(vb.elbo_trace(out['Li']))      # the one collective of the path, inside the library (NCCL)
             return out
 
+        # nvidia-smi needs up to a second before its first sample on a busy 8-GPU box: start it before the warm-up
+        sampler = ClockSampler(local_rank) if (with_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
         for _ in range(warmup):
             if flush is not None:
                 flush.zero_()
@@ -616,10 +630,10 @@ def main():
         dbg('warm-up done')
         vb.timings(reset=True)
         l0 = vb.launches
-        sampler = ClockSampler(local_rank) if (with_clocks and rank == 0) else None
         if sampler:
-            sampler.start()
-            time.sleep(0.25)
+            t_wait = time.time()
+            while not sampler.lines and time.time() - t_wait < 3.0:      # first sample in hand before the timed region
+                time.sleep(0.05)
         torch.cuda.synchronize()
         barrier()                      # every rank enters the timed region together
         torch.cuda.synchronize()
