@@ -51,7 +51,8 @@ enum vbx_flag {
 
 const char *vbx_version(void);
 
-/* Smallest supported padded state count >= n_states (4, 8, 16, 32 or 64); -1 if n_states > 64 or < 1. */
+/* Smallest supported padded state count >= n_states (4, 8, 16, 32 or 64); -1 if n_states > 64 or < 1.
+ * (Limits of the float32 kernels: S <= 64, R <= 128 and a multiple of 4.  vbx_plan_f64 / vbx_run_f64 have no such limits.) */
 int32_t vbx_padded_states(int32_t n_states);
 
 int vbx_create(int32_t device, vbx_handle_t *out);
@@ -149,6 +150,9 @@ int vbx_hard_labels(vbx_handle_t h, const float *gamma, const int32_t *n_states,
  * All arrays float64: fea [N,R] (the reference's X, VBx/VBx.py:30), Phi [R], gamma_io [N,S], pi_io [n_rec,S],
  * alpha_io / invL_io [n_rec,S,R] or NULL, Li_out [n_rec,max_iters].  Needs vbx_plan only (no vbx_prepare_*, no float32
  * workspace); `workspace` must hold vbx_f64_workspace_bytes() bytes.  Simple kernels, not tuned for throughput. */
+/* vbx_plan_f64: a plan for vbx_run_f64 ONLY, for any feature dimension R >= 1 and any state count S <= 3600 (no padding:
+ * gamma_io [N,S], pi_io [n_rec,S]) - the reference accepts any size, and so does the float64 path of the drop-in. */
+int vbx_plan_f64(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t R, int32_t S);
 int vbx_f64_workspace_bytes(vbx_handle_t h, size_t *bytes_out);
 int vbx_run_f64(vbx_handle_t h, void *workspace, size_t workspace_bytes, const double *fea, const double *Phi,
                 double *gamma_io, double *pi_io, const int32_t *n_states, double Fa, double Fb, double loop_prob,

@@ -745,8 +745,33 @@ def test_host_pipeline_equals_resident_path():
     vb.close()
 
 
+@pytest.mark.parametrize('T,R,S,precision', [(60, 200, 100, 'float64'), (90, 131, 70, 'float32'), (40, 3, 2, 'float64'), (1, 7, 65, 'float64')])
+def test_dropin_has_no_size_limits(T, R, S, precision):
+    """The reference accepts any number of states and any feature dimension; so does the drop-in: its float64 kernels
+    loop over states / features (vbx_plan_f64), and the float32 mode hands sizes beyond S = 64 / D = 128 to them."""
+    import vbx_b200.api as api
+    from oracle import vbx_oracle as po
+    rng = np.random.default_rng(T + R + S)
+    Phi = np.exp(np.linspace(np.log(5.6), np.log(0.53), R))
+    fea, _ = synth.make_recording(T, R, Phi, rng, n_spk=3)
+    g0 = synth.dirichlet_rows(T, S, rng)
+    api.set_precision(precision)
+    try:
+        g, p, L, a, il = api.VBx(fea, Phi, loopProb=0.9, Fa=0.4, Fb=11.0, pi=S, gamma=g0, maxIters=6, epsilon=1e-6, return_model=True)
+    finally:
+        api.set_precision('float64')
+    gr, pr, Lr, ar, ilr = po.vbx_oracle(fea, Phi, loopProb=0.9, Fa=0.4, Fb=11.0, pi=S, gamma=g0, maxIters=6, epsilon=1e-6, return_model=True)
+    assert g.shape == (T, S) and p.shape == (S,) and a.shape == (S, R) and len(L) == len(Lr)
+    np.testing.assert_allclose(g, gr, atol=1e-7)
+    np.testing.assert_allclose(p, pr, atol=1e-8)
+    np.testing.assert_allclose([l[0] for l in L], [l[0] for l in Lr], rtol=1e-9)
+    np.testing.assert_allclose(a, ar, atol=1e-7)
+    np.testing.assert_allclose(il, ilr, atol=1e-9)
+
+
 def test_dropin_pads_odd_feature_dims():
-    """lda_dim values that are not a multiple of 4 (VBx/vbhmm.py --lda-dim is free): zero-padded on the host."""
+    """lda_dim values that are not a multiple of 4 (VBx/vbhmm.py --lda-dim is free): float64 mode takes them as they are,
+    float32 mode zero-pads on the host."""
     from vbx_b200 import VBx
     from oracle import vbx_oracle as po
     rng = np.random.default_rng(12)

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('VBX_B200_LIB', os.path.join(_HERE, 'libvbx_b200.so'))
 EXPORTS = ['vbx_version', 'vbx_padded_states', 'vbx_create', 'vbx_destroy', 'vbx_last_error',
            'vbx_set_option', 'vbx_plan', 'vbx_bind_workspace', 'vbx_prepare_scale',
            'vbx_prepare_project', 'vbx_prepare_xvectors', 'vbx_run', 'vbx_hard_labels', 'vbx_ahc_workspace_bytes', 'vbx_ahc', 'vbx_launch_count', 'vbx_get_timings', 'vbx_f64_workspace_bytes',
-           'vbx_run_f64', 'vbx_forward_backward', 'vbx_attach_comm', 'vbx_elbo_trace']
+           'vbx_run_f64', 'vbx_plan_f64', 'vbx_forward_backward', 'vbx_attach_comm', 'vbx_elbo_trace']
 
 FLAG_NONFINITE, FLAG_ELBO_DECREASED, FLAG_CONVERGED = 1, 2, 4
 KERNEL_CLASSES = ['project', 'prepare', 'run_init', 'mstep_partial', 'speaker_model', 'loglik', 'forward_backward', 'exact64']
@@ -49,6 +49,8 @@ def load():
     lib.vbx_set_option.argtypes = [vp, ctypes.c_char_p, i32]
     lib.vbx_plan.restype = ctypes.c_int
     lib.vbx_plan.argtypes = [vp, ctypes.POINTER(i64), i32, i32, i32, ctypes.POINTER(ctypes.c_size_t)]
+    lib.vbx_plan_f64.restype = ctypes.c_int
+    lib.vbx_plan_f64.argtypes = [vp, ctypes.POINTER(i64), i32, i32, i32]
     lib.vbx_bind_workspace.restype = ctypes.c_int
     lib.vbx_bind_workspace.argtypes = [vp, vp, ctypes.c_size_t]
     lib.vbx_prepare_scale.restype = ctypes.c_int

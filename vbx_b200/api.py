@@ -86,11 +86,11 @@ _PLAN_CACHE = {}
 _PLAN_CACHE_SIZE = 8
 
 
-def _cached_batch(T, D, S, dev, allocate):
-    key = (int(T), int(D), int(S), dev.index, bool(allocate))
+def _cached_batch(T, D, S, dev, allocate, f64_only=False):
+    key = (int(T), int(D), int(S), dev.index, bool(allocate), bool(f64_only))
     vb = _PLAN_CACHE.pop(key, None)
     if vb is None:
-        vb = VbxBatch([T], D, S, device=dev, allocate=allocate)
+        vb = VbxBatch([T], D, S, device=dev, allocate=allocate, f64_only=f64_only)
         vb.rho = None
     _PLAN_CACHE[key] = vb                       # most recently used last
     while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
@@ -114,7 +114,7 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
     X = np.asarray(X)
     Phi = np.asarray(Phi)
     T, D = X.shape                                    # VBx/VBx.py:74
-    if D % 4 != 0 and D < 128:
+    if PRECISION == 'float32' and D % 4 != 0 and D < 128:
         # The kernels want a feature dimension that is a multiple of 4.  Zero features with zero across-class
         # variance are inert: invL = 1, alpha = 0, no bias, no regulariser term; only the constant D*log(2*pi) of G
         # (VBx/VBx.py:87) depends on D, which is put back into the ELBO trace below.
@@ -143,7 +143,8 @@ def VBx(X, Phi, loopProb=0.9, Fa=1.0, Fb=1.0, pi=10, gamma=None, maxIters=10,
     dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
     if dev is None:
         raise _lib.VbxError('VBx(): no CUDA device - vbx_b200 has no CPU fallback')
-    if PRECISION == 'float64':
+    if PRECISION == 'float64' or S > 64 or D > 128:
+        # float64 kernels: any number of states / features, like the reference (the float32 kernels hold S <= 64, D <= 128)
         return _vbx_f64(X, Phi, loopProb, Fa, Fb, pi, gamma, maxIters, epsilon, ref, return_model, alpha, invL, dev)
     vb = _cached_batch(T, D, S, dev, True)
     vb.set_option('gemm', 1)      # single recording: float32 FFMA contractions (closest to the float64 reference);
@@ -198,7 +199,7 @@ def _vbx_f64(X, Phi, loopProb, Fa, Fb, pi, gamma, maxIters, epsilon, ref, return
     """Float64 evaluation through vbx_run_f64 (include/vbx_b200.h)."""
     T, D = X.shape
     S = len(pi)
-    vb = _cached_batch(T, D, S, dev, False)
+    vb = _cached_batch(T, D, S, dev, False, f64_only=True)      # any S, any D: no padding (the reference has no limits)
     Sp = vb.S
     f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
     fea_d, phi_d = f64(X), f64(Phi)

@@ -22,12 +22,13 @@ def _ptr(t):
 class VbxBatch:
     """Plan + workspace for one packed ragged batch on one device."""
 
-    def __init__(self, lengths, R, n_states, device=None, allocate=True, exact_stop=True, fb_split=0, S_pad=None):
+    def __init__(self, lengths, R, n_states, device=None, allocate=True, exact_stop=True, fb_split=0, S_pad=None, f64_only=False):
         """lengths: per-recording frame counts T_b; R: feature dim seen by VBx() (VBx/VBx.py:74);
         n_states: int or per-recording ints (the `pi`-as-int / len(pi) of VBx/VBx.py:76-77).
         exact_stop: reserve the buffers of the float64 finishing phase, so that run() with a finite epsilon applies the
         reference's stop rule (VBx/VBx.py:122-125) at float64 resolution; False = float32 only (smaller workspace).
-        fb_split: 0 = auto, 1 = always, 2 = never run the forward / backward sweeps concurrently (include/vbx_b200.h)."""
+        fb_split: 0 = auto, 1 = always, 2 = never run the forward / backward sweeps concurrently (include/vbx_b200.h).
+        f64_only: plan for run_f64() only (vbx_plan_f64): any R and any number of states, no padding."""
         if not torch.cuda.is_available():
             raise VbxError('vbx_b200 needs a CUDA device (B200, sm_100); there is no CPU path')
         self.lib = _lib.load()
@@ -47,7 +48,11 @@ class VbxBatch:
         if ns.shape[0] != self.B:
             raise ValueError('n_states must be an int or one int per recording')
         self.n_states_host = ns
-        self.S = _lib.padded_states(int(ns.max()) if self.B else 1) if S_pad is None else int(S_pad)
+        self.f64_only = bool(f64_only)
+        if self.f64_only:
+            self.S = int(ns.max()) if self.B else 1
+        else:
+            self.S = _lib.padded_states(int(ns.max()) if self.B else 1) if S_pad is None else int(S_pad)
         self.uniform_states = bool(np.all(ns == self.S))
         self._h = ctypes.c_void_p()
         rc = self.lib.vbx_create(self.device.index, ctypes.byref(self._h))
@@ -57,8 +62,13 @@ class VbxBatch:
         self._check(self.lib.vbx_set_option(self._h, b'exact_stop', int(self.exact_stop)))
         self._check(self.lib.vbx_set_option(self._h, b'fb_split', int(fb_split)))
         need = ctypes.c_size_t()
-        self._check(self.lib.vbx_plan(self._h, self.offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                                      self.B, self.R, self.S, ctypes.byref(need)))
+        if self.f64_only:
+            self._check(self.lib.vbx_plan_f64(self._h, self.offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                              self.B, self.R, self.S))
+            allocate = False
+        else:
+            self._check(self.lib.vbx_plan(self._h, self.offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                          self.B, self.R, self.S, ctypes.byref(need)))
         self.workspace_bytes = int(need.value)
         with torch.cuda.device(self.device):
             self.n_states = None if self.uniform_states else torch.from_numpy(ns).to(self.device)

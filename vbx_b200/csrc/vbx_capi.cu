@@ -18,6 +18,7 @@ struct vbx_handle_s {
     vbx::Plan plan;
     vbx::Workspace ws;
     bool planned = false, bound = false, prepared = false;
+    bool f64_only = false;       // the plan came from vbx_plan_f64: any S / R, float64 entry points only
     size_t ws_need = 0;
     void *plan_mem = nullptr;  // one device allocation backing all plan arrays
     int opt_fb_spl = 0;
@@ -367,6 +368,7 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
         h->plan_mem = nullptr;
     }
     h->planned = h->bound = h->prepared = false;
+    h->f64_only = false;
     e = cudaMalloc(&h->plan_mem, off);
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(plan)");
     char *base = static_cast<char *>(h->plan_mem);
@@ -420,9 +422,42 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
     return VBX_OK;
 }
 
+int vbx_plan_f64(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t R, int32_t S) {
+    if (!h || !offsets_host || n_rec < 0) return fail(h, VBX_ERR_ARG, "vbx_plan_f64: null argument");
+    if (R < 1 || S < 1 || S > 3600) return fail(h, VBX_ERR_ARG, "vbx_plan_f64: need R >= 1 and 1 <= S <= 3600");
+    if (n_rec > 0 && offsets_host[0] != 0) return fail(h, VBX_ERR_ARG, "vbx_plan_f64: offsets[0] must be 0");
+    for (int b = 0; b < n_rec; ++b) {
+        const int64_t T = offsets_host[b + 1] - offsets_host[b];
+        if (T < 0 || T > (int64_t)1 << 30) return fail(h, VBX_ERR_ARG, "vbx_plan_f64: bad recording length");
+    }
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return cuda_fail(h, guard.err, "cudaSetDevice");
+    if (h->plan_mem) {
+        cudaFree(h->plan_mem);
+        h->plan_mem = nullptr;
+    }
+    h->planned = h->bound = h->prepared = false;
+    cudaError_t e = cudaMalloc(&h->plan_mem, sizeof(int64_t) * (n_rec + 1));
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(plan)");
+    e = cudaMemcpy(h->plan_mem, offsets_host, sizeof(int64_t) * (n_rec + 1), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemcpy(plan)");
+    h->plan = vbx::Plan();
+    h->plan.n_rec = n_rec;
+    h->plan.R = R;
+    h->plan.S = S;
+    h->plan.n_frames = n_rec ? offsets_host[n_rec] : 0;
+    h->plan.offsets = static_cast<const int64_t *>(h->plan_mem);
+    h->offsets_host.assign(offsets_host, offsets_host + n_rec + 1);
+    h->ahc_need = 0;
+    h->planned = true;
+    h->f64_only = true;
+    return VBX_OK;
+}
+
 int vbx_bind_workspace(vbx_handle_t h, void *workspace, size_t bytes) {
     if (!h) return VBX_ERR_ARG;
     if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_bind_workspace: call vbx_plan first");
+    if (h->f64_only) return fail(h, VBX_ERR_STATE, "vbx_bind_workspace: the plan came from vbx_plan_f64 (float64 entry points only)");
     if (!workspace || bytes < h->ws_need) return fail(h, VBX_ERR_STATE, "vbx_bind_workspace: workspace too small");
     const size_t mis = reinterpret_cast<uintptr_t>(workspace) & 255;
     char *base = static_cast<char *>(workspace) + (mis ? 256 - mis : 0);
@@ -657,7 +692,7 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
 int vbx_hard_labels(vbx_handle_t h, const float *gamma, const int32_t *n_states, int32_t *first_out,
                     int32_t *second_out, void *stream) {
     if (!h) return VBX_ERR_ARG;
-    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_hard_labels: call vbx_plan first");
+    if (!h->planned || h->f64_only) return fail(h, VBX_ERR_STATE, "vbx_hard_labels: call vbx_plan first");
     if (h->plan.n_frames && (!gamma || !first_out)) return fail(h, VBX_ERR_ARG, "vbx_hard_labels: null pointer");
     DeviceGuard guard(h->device);
     return counted(h, vbx::launch_hard_labels(h->plan, gamma, n_states, first_out, second_out, (cudaStream_t)stream), "hard_labels");
@@ -665,7 +700,7 @@ int vbx_hard_labels(vbx_handle_t h, const float *gamma, const int32_t *n_states,
 
 int vbx_ahc_workspace_bytes(vbx_handle_t h, size_t *bytes_out) {
     if (!h || !bytes_out) return VBX_ERR_ARG;
-    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_ahc_workspace_bytes: call vbx_plan first");
+    if (!h->planned || h->f64_only) return fail(h, VBX_ERR_STATE, "vbx_ahc_workspace_bytes: call vbx_plan first");
     *bytes_out = h->ahc_need;
     return VBX_OK;
 }
@@ -674,7 +709,7 @@ int vbx_ahc(vbx_handle_t h, const void *x, int32_t x_is_f64, int32_t dim, void *
             double *Z_out, double *thr_out, void *stream) {
     if (!h) return VBX_ERR_ARG;
     Range nvtx_range("vbx_ahc");
-    if (!h->planned) return fail(h, VBX_ERR_STATE, "vbx_ahc: call vbx_plan first");
+    if (!h->planned || h->f64_only) return fail(h, VBX_ERR_STATE, "vbx_ahc: call vbx_plan first");
     if (dim < 1) return fail(h, VBX_ERR_ARG, "vbx_ahc: dim < 1");
     if (h->plan.n_rec == 0) return VBX_OK;
     if (!workspace || !thr_out || (h->plan.n_frames && (!x || !Z_out))) return fail(h, VBX_ERR_ARG, "vbx_ahc: null pointer");

@@ -5,7 +5,9 @@
 // |ELBO| ~ 1e5.  This path keeps every quantity in float64 so that the drop-in VBx() reproduces the reference's
 // iteration count and its gamma / pi / Li to ~1e-9.  It is deliberately simple (a handful of straightforward
 // kernels, scaled linear-domain recursion with the same O(S) transition structure as the float32 path): it is meant
-// for the one-recording-per-call use of VBx/vbhmm.py:154-158, not for throughput.
+// for the one-recording-per-call use of VBx/vbhmm.py:154-158, not for throughput.  Like the reference it accepts ANY number
+// of HMM states and ANY feature dimension (vbx_plan_f64): every kernel loops over states / features instead of fixing a
+// lane per state.
 #include <math_constants.h>
 
 #include "vbx_internal.cuh"
@@ -67,31 +69,32 @@ __global__ void __launch_bounds__(128) prep_kernel(Plan pl, Buffers b, const dou
     }
 }
 
-// M-step for one (recording, speaker): invL, alpha over r                     VBx/VBx.py:95-96
+// M-step for one (recording, speaker): invL, alpha over r (threads stride the features)      VBx/VBx.py:95-96
 __global__ void __launch_bounds__(128) mstep_kernel(Plan pl, Buffers b, const double *__restrict__ gamma,
                                                     const double *__restrict__ Phi, const int32_t *n_states, double FaFb) {
     const int rec = blockIdx.x / pl.S, s = blockIdx.x % pl.S;
     if (!b.active[rec]) return;
-    const int R = pl.R, S = pl.S, r = threadIdx.x;
+    const int R = pl.R, S = pl.S;
     const int ns = n_states ? n_states[rec] : S;
     const int64_t f0 = pl.offsets[rec];
     const int64_t T = pl.offsets[rec + 1] - f0;
-    if (r >= R) return;
-    const int64_t o = ((int64_t)rec * S + s) * R + r;
-    if (s >= ns) {
-        b.alpha[o] = 0.0;
-        b.invL[o] = 0.0;
-        return;
+    for (int r = threadIdx.x; r < R; r += 128) {
+        const int64_t o = ((int64_t)rec * S + s) * R + r;
+        if (s >= ns) {
+            b.alpha[o] = 0.0;
+            b.invL[o] = 0.0;
+            continue;
+        }
+        double Ns = 0.0, gr = 0.0;
+        for (int64_t t = 0; t < T; ++t) {
+            const double g = gamma[(f0 + t) * S + s];
+            Ns += g;
+            gr += g * b.rho[(f0 + t) * R + r];
+        }
+        const double iL = 1.0 / (1.0 + FaFb * Ns * Phi[r]);
+        b.invL[o] = iL;
+        b.alpha[o] = FaFb * iL * gr;
     }
-    double Ns = 0.0, gr = 0.0;
-    for (int64_t t = 0; t < T; ++t) {
-        const double g = gamma[(f0 + t) * S + s];
-        Ns += g;
-        gr += g * b.rho[(f0 + t) * R + r];
-    }
-    const double iL = 1.0 / (1.0 + FaFb * Ns * Phi[r]);
-    b.invL[o] = iL;
-    b.alpha[o] = FaFb * iL * gr;
 }
 
 // per-speaker bias of eq. (23) and the ELBO regulariser of eq. (25)           VBx/VBx.py:97,100
@@ -100,22 +103,24 @@ __global__ void __launch_bounds__(128) bias_kernel(Plan pl, Buffers b, const dou
     __shared__ double sh[4];
     const int rec = blockIdx.x;
     if (!b.active[rec]) return;
-    const int R = pl.R, S = pl.S, r = threadIdx.x;
+    const int R = pl.R, S = pl.S;
     const int ns = n_states ? n_states[rec] : S;
     double reg = 0.0;
     for (int s = 0; s < S; ++s) {
         double c = 0.0;
-        if (s < ns && r < R) {
-            const int64_t o = ((int64_t)rec * S + s) * R + r;
-            const double iL = b.invL[o], a = b.alpha[o];
-            c = (iL + a * a) * Phi[r];
-            reg += log(iL) - iL - a * a + 1.0;
+        if (s < ns) {
+            for (int r = threadIdx.x; r < R; r += 128) {
+                const int64_t o = ((int64_t)rec * S + s) * R + r;
+                const double iL = b.invL[o], a = b.alpha[o];
+                c += (iL + a * a) * Phi[r];
+                reg += log(iL) - iL - a * a + 1.0;
+            }
         }
         c = block_sum(c, sh);
-        if (r == 0) b.bias[(int64_t)rec * S + s] = s < ns ? 0.5 * c : CUDART_INF;
+        if (threadIdx.x == 0) b.bias[(int64_t)rec * S + s] = s < ns ? 0.5 * c : CUDART_INF;
     }
     reg = block_sum(reg, sh);
-    if (r == 0) b.reg[rec] = 0.5 * Fb * reg;
+    if (threadIdx.x == 0) b.reg[rec] = 0.5 * Fb * reg;
 }
 
 // log-likelihoods, row max, exp: one thread per frame                          VBx/VBx.py:97
@@ -149,80 +154,80 @@ __global__ void __launch_bounds__(128) loglik_kernel(Plan pl, Buffers b, double 
     b.rowmax[f] = m;
 }
 
-// forward-backward, pi, ELBO, stop rule: one warp per recording, lane = state (two states per lane for S = 64)
-// VBx/VBx.py:98-105,122-125,146-175 in the scaled linear domain (see vbx_kernels.cu for the derivation)
+// forward-backward, pi, ELBO, stop rule: one warp per recording, lanes stride the states (any S: the per-state vectors
+// live in shared memory)            VBx/VBx.py:98-105,122-125,146-175 in the scaled linear domain (see vbx_kernels.cu)
 __global__ void __launch_bounds__(32) fb_kernel(Plan pl, Buffers b, double *gamma, double *pi_io, const int32_t *n_states,
                                                 double Fa, double loopP, double epsilon, double *Li, int32_t *n_iters,
                                                 int32_t *flags, int iter, int max_iters) {
+    extern __shared__ double shv[];
     const int rec = blockIdx.x, lane = threadIdx.x;
     if (!b.active[rec]) return;
     const int S = pl.S;
+    double *pi = shv, *w = shv + S, *base = shv + 2 * S, *a = shv + 3 * S, *bb = shv + 4 * S, *enter = shv + 5 * S, *g0 = shv + 6 * S;
     const int ns = n_states ? n_states[rec] : S;
     const int64_t f0 = pl.offsets[rec];
     const int T = (int)(pl.offsets[rec + 1] - f0);
     const double P = loopP, Q = 1.0 - loopP, eps = 1e-8;
-    double pi[2], w[2], a[2], base[2];
-    for (int k = 0; k < 2; ++k) {
-        const int s = lane + 32 * k;
+    for (int s = lane; s < S; s += 32) {
         const bool live = s < ns;
-        pi[k] = live ? pi_io[(int64_t)rec * S + s] : 0.0;
-        w[k] = live ? Q * pi[k] + eps : 0.0;
-        base[k] = live ? pi[k] + eps : 0.0;
-        a[k] = 0.0;
+        pi[s] = live ? pi_io[(int64_t)rec * S + s] : 0.0;
+        w[s] = live ? Q * pi[s] + eps : 0.0;
+        base[s] = live ? pi[s] + eps : 0.0;
+        a[s] = 0.0;
+        enter[s] = 0.0;
     }
+    __syncwarp();
     const double *pp = b.p + f0 * S;
     double *ga = gamma + f0 * S;
     double tll = 0.0;
     for (int t = 0; t < T; ++t) {
-        double v[2], loc = 0.0;
-        for (int k = 0; k < 2; ++k) {
-            const int s = lane + 32 * k;
-            v[k] = s < S ? pp[(int64_t)t * S + s] * base[k] : 0.0;
-            loc += v[k];
+        double loc = 0.0;
+        for (int s = lane; s < S; s += 32) {
+            const double v = pp[(int64_t)t * S + s] * base[s];
+            a[s] = v;
+            loc += v;
         }
         const double sig = warp_sum(loc);
         const double r = 1.0 / sig;
-        for (int k = 0; k < 2; ++k) {
-            const int s = lane + 32 * k;
-            a[k] = v[k] * r;
-            base[k] = P * a[k] + w[k] * 1.0;
-            if (s < S) ga[(int64_t)t * S + s] = a[k];
+        for (int s = lane; s < S; s += 32) {
+            const double av = a[s] * r;
+            a[s] = av;
+            base[s] = P * av + w[s];
+            ga[(int64_t)t * S + s] = av;
         }
         if (lane == 0) b.rsig[f0 + t] = r;
         tll += log(sig) + b.rowmax[f0 + t];
     }
     __syncwarp();
-    double bb[2] = {1.0, 1.0}, g0[2] = {a[0], a[1]}, occ[2] = {a[0], a[1]}, enter[2] = {0.0, 0.0};
+    for (int s = lane; s < S; s += 32) {
+        bb[s] = 1.0;
+        g0[s] = a[s];
+    }
     for (int t = T - 2; t >= 0; --t) {
         const double cr = b.rsig[f0 + t + 1];
-        double u[2], loc = 0.0;
-        for (int k = 0; k < 2; ++k) {
-            const int s = lane + 32 * k;
-            u[k] = s < S ? pp[(int64_t)(t + 1) * S + s] * bb[k] * cr : 0.0;
-            loc += w[k] * u[k];
+        double loc = 0.0;
+        for (int s = lane; s < S; s += 32) {
+            const double u = pp[(int64_t)(t + 1) * S + s] * bb[s] * cr;
+            a[s] = u;                       // a[] is free now: holds u for the second pass
+            loc += w[s] * u;
         }
         const double dot = warp_sum(loc);
-        for (int k = 0; k < 2; ++k) {
-            const int s = lane + 32 * k;
-            enter[k] += u[k];
-            bb[k] = P * u[k] + dot;
-            if (s < S) {
-                g0[k] = ga[(int64_t)t * S + s] * bb[k];
-                ga[(int64_t)t * S + s] = g0[k];
-                occ[k] += g0[k];
-            }
+        for (int s = lane; s < S; s += 32) {
+            const double u = a[s];
+            enter[s] += u;
+            bb[s] = P * u + dot;
+            g0[s] = ga[(int64_t)t * S + s] * bb[s];
+            ga[(int64_t)t * S + s] = g0[s];
         }
     }
-    double pn[2], loc = 0.0;
-    for (int k = 0; k < 2; ++k) {
-        pn[k] = g0[k] + Q * pi[k] * enter[k];
-        loc += pn[k];
+    double loc = 0.0;
+    for (int s = lane; s < S; s += 32) {
+        const double pn = g0[s] + Q * pi[s] * enter[s];
+        a[s] = pn;
+        loc += pn;
     }
     const double tot = warp_sum(loc);
-    for (int k = 0; k < 2; ++k) {
-        const int s = lane + 32 * k;
-        if (s < S) pi_io[(int64_t)rec * S + s] = pn[k] / tot;
-    }
+    for (int s = lane; s < S; s += 32) pi_io[(int64_t)rec * S + s] = a[s] / tot;
     if (lane == 0) {
         const double elbo = tll + Fa * b.gsum[rec] + b.reg[rec];
         Li[(int64_t)rec * max_iters + iter] = elbo;
@@ -276,6 +281,15 @@ int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const dou
         cudaMemcpyAsync(b.invL, invL_io, sizeof(double) * B * S * R, cudaMemcpyDeviceToDevice, st);
     }
     const int fblocks = (int)((pl.n_frames + 127) / 128);
+    const size_t fb_smem = (size_t)7 * pl.S * sizeof(double);     // per-state vectors of the sweep
+    if (fb_smem > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            if (cudaFuncSetAttribute(f64::fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+            configured = true;
+        }
+        if (fb_smem > 200 * 1024) return -1;                      // more than 3600 states
+    }
     for (int it = 0; it < max_iters; ++it) {
         if (!(it == 0 && warm)) {
             f64::mstep_kernel<<<pl.n_rec * pl.S, 128, 0, st>>>(pl, b, gamma, Phi, n_states, Fa / Fb);
@@ -283,7 +297,7 @@ int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const dou
         }
         f64::bias_kernel<<<pl.n_rec, 128, 0, st>>>(pl, b, Phi, n_states, Fb);
         if (fblocks) f64::loglik_kernel<<<fblocks, 128, 0, st>>>(pl, b, Fa);
-        f64::fb_kernel<<<pl.n_rec, 32, 0, st>>>(pl, b, gamma, pi, n_states, Fa, loopP, epsilon, Li, n_iters, flags, it, max_iters);
+        f64::fb_kernel<<<pl.n_rec, 32, fb_smem, st>>>(pl, b, gamma, pi, n_states, Fa, loopP, epsilon, Li, n_iters, flags, it, max_iters);
         launches += 3;
     }
     if (alpha_io && invL_io) {
