@@ -154,6 +154,100 @@ __global__ void __launch_bounds__(128) loglik_kernel(Plan pl, Buffers b, double 
     b.rowmax[f] = m;
 }
 
+// forward-backward, pi, ELBO, stop rule for S <= 64: one warp per recording, lane = state (two states per lane for
+// S > 32), everything in registers
+// VBx/VBx.py:98-105,122-125,146-175 in the scaled linear domain (see vbx_kernels.cu for the derivation)
+__global__ void __launch_bounds__(32) fb_kernel_small(Plan pl, Buffers b, double *gamma, double *pi_io, const int32_t *n_states,
+                                                double Fa, double loopP, double epsilon, double *Li, int32_t *n_iters,
+                                                int32_t *flags, int iter, int max_iters) {
+    const int rec = blockIdx.x, lane = threadIdx.x;
+    if (!b.active[rec]) return;
+    const int S = pl.S;
+    const int ns = n_states ? n_states[rec] : S;
+    const int64_t f0 = pl.offsets[rec];
+    const int T = (int)(pl.offsets[rec + 1] - f0);
+    const double P = loopP, Q = 1.0 - loopP, eps = 1e-8;
+    double pi[2], w[2], a[2], base[2];
+    for (int k = 0; k < 2; ++k) {
+        const int s = lane + 32 * k;
+        const bool live = s < ns;
+        pi[k] = live ? pi_io[(int64_t)rec * S + s] : 0.0;
+        w[k] = live ? Q * pi[k] + eps : 0.0;
+        base[k] = live ? pi[k] + eps : 0.0;
+        a[k] = 0.0;
+    }
+    const double *pp = b.p + f0 * S;
+    double *ga = gamma + f0 * S;
+    double tll = 0.0;
+    for (int t = 0; t < T; ++t) {
+        double v[2], loc = 0.0;
+        for (int k = 0; k < 2; ++k) {
+            const int s = lane + 32 * k;
+            v[k] = s < S ? pp[(int64_t)t * S + s] * base[k] : 0.0;
+            loc += v[k];
+        }
+        const double sig = warp_sum(loc);
+        const double r = 1.0 / sig;
+        for (int k = 0; k < 2; ++k) {
+            const int s = lane + 32 * k;
+            a[k] = v[k] * r;
+            base[k] = P * a[k] + w[k] * 1.0;
+            if (s < S) ga[(int64_t)t * S + s] = a[k];
+        }
+        if (lane == 0) b.rsig[f0 + t] = r;
+        tll += log(sig) + b.rowmax[f0 + t];
+    }
+    __syncwarp();
+    double bb[2] = {1.0, 1.0}, g0[2] = {a[0], a[1]}, occ[2] = {a[0], a[1]}, enter[2] = {0.0, 0.0};
+    for (int t = T - 2; t >= 0; --t) {
+        const double cr = b.rsig[f0 + t + 1];
+        double u[2], loc = 0.0;
+        for (int k = 0; k < 2; ++k) {
+            const int s = lane + 32 * k;
+            u[k] = s < S ? pp[(int64_t)(t + 1) * S + s] * bb[k] * cr : 0.0;
+            loc += w[k] * u[k];
+        }
+        const double dot = warp_sum(loc);
+        for (int k = 0; k < 2; ++k) {
+            const int s = lane + 32 * k;
+            enter[k] += u[k];
+            bb[k] = P * u[k] + dot;
+            if (s < S) {
+                g0[k] = ga[(int64_t)t * S + s] * bb[k];
+                ga[(int64_t)t * S + s] = g0[k];
+                occ[k] += g0[k];
+            }
+        }
+    }
+    double pn[2], loc = 0.0;
+    for (int k = 0; k < 2; ++k) {
+        pn[k] = g0[k] + Q * pi[k] * enter[k];
+        loc += pn[k];
+    }
+    const double tot = warp_sum(loc);
+    for (int k = 0; k < 2; ++k) {
+        const int s = lane + 32 * k;
+        if (s < S) pi_io[(int64_t)rec * S + s] = pn[k] / tot;
+    }
+    if (lane == 0) {
+        const double elbo = tll + Fa * b.gsum[rec] + b.reg[rec];
+        Li[(int64_t)rec * max_iters + iter] = elbo;
+        n_iters[rec] = iter + 1;
+        int fl = flags[rec];
+        if (!isfinite(elbo)) fl |= 1;
+        if (iter > 0) {
+            const double d = elbo - b.prev[rec];
+            if (d < epsilon) {
+                b.active[rec] = 0;
+                if (iter + 1 < max_iters) fl |= 4;
+                if (d < 0.0) fl |= 2;
+            }
+        }
+        b.prev[rec] = elbo;
+        flags[rec] = fl;
+    }
+}
+
 // forward-backward, pi, ELBO, stop rule: one warp per recording, lanes stride the states (any S: the per-state vectors
 // live in shared memory)            VBx/VBx.py:98-105,122-125,146-175 in the scaled linear domain (see vbx_kernels.cu)
 __global__ void __launch_bounds__(32) fb_kernel(Plan pl, Buffers b, double *gamma, double *pi_io, const int32_t *n_states,
@@ -297,7 +391,10 @@ int launch_run_f64(const Plan &pl, void *workspace, const double *fea, const dou
         }
         f64::bias_kernel<<<pl.n_rec, 128, 0, st>>>(pl, b, Phi, n_states, Fb);
         if (fblocks) f64::loglik_kernel<<<fblocks, 128, 0, st>>>(pl, b, Fa);
-        f64::fb_kernel<<<pl.n_rec, 32, fb_smem, st>>>(pl, b, gamma, pi, n_states, Fa, loopP, epsilon, Li, n_iters, flags, it, max_iters);
+        if (pl.S <= 64)
+            f64::fb_kernel_small<<<pl.n_rec, 32, 0, st>>>(pl, b, gamma, pi, n_states, Fa, loopP, epsilon, Li, n_iters, flags, it, max_iters);
+        else
+            f64::fb_kernel<<<pl.n_rec, 32, fb_smem, st>>>(pl, b, gamma, pi, n_states, Fa, loopP, epsilon, Li, n_iters, flags, it, max_iters);
         launches += 3;
     }
     if (alpha_io && invL_io) {
