@@ -75,6 +75,30 @@ def test_forward_backward_sweeps(sass):
         assert c['MUFU'] > 0, f
 
 
+def test_split_sweeps_and_float64_finish(sass):
+    sw = functions(sass, 'fb_sweeps_kernel')
+    assert len(sw) >= 5                                     # S = 4 ... 64 (+ the states-per-lane variants)
+    for f, c in sw.items():
+        assert c['LDG.E.64.STRONG.SYS'] + c['LDG.E.STRONG.SYS'] + c['LDG.E.128.STRONG.SYS'] > 0, f   # order-pinned bursts
+        assert c['SHFL'] > 0 and c['MUFU'] > 0, f           # group reductions, off-chain reciprocals
+    assert functions(sass, 'fb_combine_kernel') and functions(sass, 'fb_split_tail_kernel')
+    for name in ('mstep64_kernel', 'loglik64_kernel', 'fb64_kernel', 'speaker64_kernel', 'fb_dense_kernel'):
+        fns = functions(sass, name)
+        assert fns, name
+        for f, c in fns.items():
+            assert c['DFMA'] + c['DADD'] + c['DMUL'] > 0, f  # float64 arithmetic
+    assert functions(sass, 'elbo_trace_kernel') and functions(sass, 'snapshot_kernel')
+
+
+def test_front_end_uses_the_three_way_split(sass):
+    """The two passes of the real-data front end issue six tcgen05.mma per k-step (x3 v1, x1 v3, x2 v2, x2 v1, x1 v2, x1 v1)
+    on one 128-row M-tile; the headline projection three on two M-tiles: 24 per 32-column block either way."""
+    proj = functions(sass, 'project_tcgen05_kernel')
+    three = [f for f in proj if 'ILi1ELi3E' in f or 'ILi2ELi3E' in f]
+    two = [f for f in proj if 'ILi0ELi2E' in f]
+    assert len(three) == 2 and len(two) == 1, list(proj)
+
+
 def test_float64_ahc_kernels(sass):
     assert functions(sass, 'ahc_cosine_kernel') and functions(sass, 'ahc_linkage_kernel')
     for f, c in functions(sass, 'ahc_cosine_kernel').items():
