@@ -372,6 +372,21 @@ def test_stop_rule_of_a_batch_matches_the_float64_oracle(eps, S, hp):
         assert np.array_equal(one['gamma'], out['gamma'][lo:hi]) and np.array_equal(one['Li'][0], out['Li'][b], equal_nan=True)
 
 
+@pytest.mark.parametrize('eps', [1e-3, 1e-5])
+def test_stop_rule_many_tiny_recordings(eps):
+    """Very short recordings have a small |ELBO| and therefore the tightest float32 noise bound: 300 recordings of 1 .. 40
+    frames must all stop at the float64 oracle's iteration."""
+    rng = np.random.default_rng(8)
+    lens = rng.integers(1, 41, size=300)
+    S = 5
+    d = synth.make_batch(lens, R=128, S=S, seed=808, dtype=np.float32)
+    ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(S, 1.0 / S), 0.3, 17.0, 0.9, 40, eps)
+    out = run_gpu(d['fea'], d['Phi'], lens, d['gamma0'], Fa=0.3, Fb=17.0, loopProb=0.9, maxIters=40, epsilon=eps)
+    bad = np.nonzero(out['n_iters'] != ref['n_iters'])[0]
+    assert len(bad) == 0, [(int(b), int(lens[b]), int(out['n_iters'][b]), int(ref['n_iters'][b])) for b in bad[:10]]
+    assert np.abs(out['gamma'] - ref['gamma']).max() <= G_TOL
+
+
 def test_stop_rule_long_recording_and_model_output():
     """A recording that takes the chunked-scan path in float32 finishes sequentially in float64; alpha / invL returned
     with return_model come from the last (float64) M-step."""

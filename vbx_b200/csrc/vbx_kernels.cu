@@ -1275,7 +1275,7 @@ __global__ void __launch_bounds__(128) elbo_kernel(Plan pl, Workspace ws, RunPar
             // float32 resolves an ELBO difference to about nb; decide here only what is decided safely
             const double nb = rp.noise_c * 5.9604644775390625e-8 * fabs(elbo);
             const bool go_on = d >= rp.epsilon + rp.guard_mult * nb;     // far above epsilon: keep iterating in float32
-            const bool stop = d < rp.epsilon - nb;                        // clearly below epsilon: the reference stops too
+            const bool stop = d < rp.epsilon - 4.0 * nb;                  // clearly below epsilon: the reference stops too
             if (!go_on && !stop) {
                 // Hand the recording to the float64 kernels (vbx_exact64.cu).  This iteration AND the previous one are
                 // discarded and redone there from the snapshot that entered iteration iter-1, so that the test of
@@ -1286,7 +1286,7 @@ __global__ void __launch_bounds__(128) elbo_kernel(Plan pl, Workspace ws, RunPar
                 ws.active[rec] = 0;
                 ws.active64[rec] = 1;
                 if (iter == 1 && rp.warm) {
-                    ws.fresh[rec] = d >= rp.epsilon + nb ? 1 : 2;
+                    ws.fresh[rec] = d >= rp.epsilon + 4.0 * nb ? 1 : 2;
                 } else {
                     ws.fresh[rec] = 1;
                     n_iters[rec] = iter - 1;
