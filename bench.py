@@ -769,7 +769,8 @@ def main():
     if not args.no_e2e and args.front == 'project':
         numa = {}
         with numa_affinity(local_rank, numa):       # pinned buffers + feeding thread on the GPU's NUMA node
-            hp = HostPipeline(res['lengths'], D_RAW, R_DIM, w['S'], device=device)
+            hp = HostPipeline(res['lengths'], D_RAW, R_DIM, w['S'], device=device,
+                              n_chunks=int(os.environ['VBX_E2E_CHUNKS']) if os.environ.get('VBX_E2E_CHUNKS') else None)
             Xh = torch.empty((N, D_RAW), dtype=torch.float32).pin_memory()
             Gh = torch.empty((N, w['S']), dtype=torch.float32).pin_memory()
             Xh.copy_(res['data']['X'])
