@@ -68,3 +68,33 @@ def test_two_rank_gloo_matches_single_process():
     ref = c_oracle.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(4, 0.25), 0.3, 17.0, 0.9, 4, -np.inf)
     np.testing.assert_allclose(elbo_sum, ref['Li'].sum(0), rtol=1e-12)
     assert np.all(n_active == len(lens))
+
+
+def test_strong_scaling_job_is_the_same_for_every_world_size():
+    """bench.py --workload c4 (strong scaling): recording i of the job is generated from seed + i whichever rank owns it,
+    and the LPT shards cover the job exactly once - so 1, 2, 4 and 8 ranks time the SAME 192 recordings."""
+    import importlib.util
+    import os
+    import torch
+    from vbx_b200 import shard
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w = dict(bench.WORKLOADS['tinystrong'])
+    lengths = bench.workload_lengths(w, seed=1000)
+    dev = torch.device('cpu')
+    whole = bench.make_device_shard(lengths, list(range(len(lengths))), w['S'], seed=17, device=dev)
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    for world in (2, 4):
+        parts = shard.partition(lengths, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(lengths)))
+        loads = [int(lengths[p].sum()) for p in parts]
+        assert max(loads) - min(loads) <= int(lengths.max())               # LPT balance
+        for p in parts:
+            mine = bench.make_device_shard(lengths, p, w['S'], seed=17, device=dev)
+            o = 0
+            for i in p:
+                n = int(lengths[i])
+                assert torch.equal(mine['X'][o:o + n], whole['X'][offs[i]:offs[i + 1]])
+                assert torch.equal(mine['gamma0'][o:o + n], whole['gamma0'][offs[i]:offs[i + 1]])
+                o += n
