@@ -68,6 +68,10 @@ const char *vbx_last_error(vbx_handle_t h);
  * recording concurrently on separate warps followed by a combine pass (the choice for batches too small to fill the GPU;
  * results differ from the fused sweep by float32 rounding only, so pin it to 1 or 2 where bit-identical results for a
  * recording alone / inside a large batch matter).
+ * "graph": 0 = auto (small batches: plans on the split schedule), 1 = always, 2 = never replay a whole vbx_run as ONE CUDA
+ * graph launch.  The second call with identical arguments (pointers and scalars) is captured on a stream of the handle,
+ * later identical calls replay it (ordered against `stream` with events, no host synchronisation); any other call, and
+ * any failure to capture, launches the kernels directly.  Off while "timing" is on.
  * "fb_priority": 0 = auto (large batches), 1 = always, 2 = never launch the forward-backward sweep on a high-priority side
  * stream of the handle (ordered against `stream` with events, still no host synchronisation), so that it interleaves with
  * the bandwidth-bound kernels of ANOTHER handle working on the same device (vbx_b200/parts.py runs two halves of a batch).

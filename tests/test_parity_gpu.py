@@ -322,6 +322,55 @@ def test_partitioned_batch_equals_the_whole_batch():
     assert len(set(results[0][4].tolist())) > 1          # recordings stopped at different iterations
 
 
+@pytest.mark.parametrize('eps', [-np.inf, 1e-5])
+def test_cuda_graph_replay_is_identical(eps):
+    """Option 'graph' (auto for small batches): the second call with identical arguments is captured, later ones replay the
+    whole run as one CUDA graph launch.  Results equal the directly launched first run bit for bit, through both stop-rule
+    phases; a call with different arguments falls back to direct launches."""
+    from vbx_b200.batch import VbxBatch
+    S = 6
+    lens, d = ragged_batch(14, S, seed=71, tmax=400)
+    vb = VbxBatch(lens, 128, S, device=dev())
+    vb.set_option('graph', 1)
+    g0 = torch.zeros((int(lens.sum()), vb.S), device=dev())
+    g0[:, :S] = cuda(d['gamma0'])
+    g, p = torch.empty_like(g0), torch.empty((len(lens), vb.S), device=dev())
+    vb.prepare_scale(cuda(d['fea']), cuda(d['Phi']))
+    # fixed output buffers: identical pointers from call to call (run() allocates Li / n_iters / flags itself, so bind them)
+    outs, launches = [], []
+    import ctypes
+    Li = torch.empty((len(lens), 30), dtype=torch.float64, device=dev())
+    ni = torch.empty(len(lens), dtype=torch.int32, device=dev())
+    fl = torch.empty(len(lens), dtype=torch.int32, device=dev())
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    for rep in range(5):
+        g.copy_(g0)
+        p.zero_()
+        p[:, :S] = 1.0 / S
+        l0 = vb.launches
+        vb._check(vb.lib.vbx_run(vb._h, ptr(vb.rho), ptr(vb.Phi), ptr(g), ptr(p), None, 0.3, 17.0, 0.99, 30, float(eps), None, None, 0,
+                                 ptr(Li), ptr(ni), ptr(fl), vb._stream()))
+        torch.cuda.synchronize()
+        launches.append(vb.launches - l0)
+        outs.append([t.clone().cpu().numpy() for t in (g, p, Li, ni, fl)])
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b, equal_nan=True)
+    assert len(set(launches)) == 1 and launches[0] > 30           # the counter counts the kernels a replay runs
+    ref = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(S, 1.0 / S), 0.3, 17.0, 0.99, 30, eps)
+    assert np.array_equal(outs[0][3], ref['n_iters'])
+    assert np.abs(outs[0][0][:, :S] - ref['gamma']).max() <= G_TOL
+    # different arguments on the same handle: direct launches again, still right
+    g.copy_(g0)
+    p.zero_()
+    p[:, :S] = 1.0 / S
+    out = vb.run(g, p, Fa=0.3, Fb=17.0, loopProb=0.9, maxIters=5, epsilon=-np.inf)
+    ref2 = co.vbx_oracle_batch(d['fea'], d['Phi'], d['offsets'], d['gamma0'], np.full(S, 1.0 / S), 0.3, 17.0, 0.9, 5, -np.inf)
+    torch.cuda.synchronize()
+    assert np.abs(g[:, :S].double().cpu().numpy() - ref2['gamma']).max() <= G_TOL
+    vb.close()
+
+
 def test_small_feature_dims():
     for R in (16, 32, 64):
         lens, d = ragged_batch(6, 5, seed=50 + R, tmax=200, R=R)

@@ -216,11 +216,20 @@ class VbxBatch:
         self.rho, self.Phi = rho, plda_psi
         return rho, x_norm
 
+    def output_buffers(self, maxIters):
+        """Preallocated outputs for run(buffers=...): with the same tensors every call the library sees identical
+        arguments and replays the whole run as one CUDA graph (option 'graph')."""
+        dev = self.device
+        return dict(Li=torch.empty((self.B, max(int(maxIters), 1)), dtype=torch.float64, device=dev),
+                    n_iters=torch.empty(self.B, dtype=torch.int32, device=dev),
+                    flags=torch.empty(self.B, dtype=torch.int32, device=dev))
+
     # ---- VBx/VBx.py:91-125 ----------------------------------------------------------------
     def run(self, gamma, pi, Fa=1.0, Fb=1.0, loopProb=0.9, maxIters=10, epsilon=1e-4,
-            alpha=None, invL=None, warm_start=False, return_model=False):
+            alpha=None, invL=None, warm_start=False, return_model=False, buffers=None):
         """gamma [N,S] and pi [B,S] float32 CUDA tensors, updated IN PLACE (padded columns must be 0).
-        Returns dict(gamma, pi, Li [B,maxIters] float64 (NaN padded), n_iters [B], flags [B][, alpha, invL])."""
+        Returns dict(gamma, pi, Li [B,maxIters] float64 (NaN padded), n_iters [B], flags [B][, alpha, invL]).
+        buffers: optional dict(Li, n_iters, flags) of preallocated output tensors (see `output_buffers`)."""
         if self.rho is None:
             raise VbxError('call prepare_scale() or prepare_project() first')
         self._f32(gamma, (self.N, self.S), 'gamma')
@@ -233,9 +242,13 @@ class VbxBatch:
                 invL = torch.zeros((self.B, self.S, self.R), dtype=torch.float32, device=dev)
             self._f32(alpha, (self.B, self.S, self.R), 'alpha')
             self._f32(invL, (self.B, self.S, self.R), 'invL')
-        Li = torch.empty((self.B, max(int(maxIters), 1)), dtype=torch.float64, device=dev)
-        n_iters = torch.empty(self.B, dtype=torch.int32, device=dev)
-        flags = torch.empty(self.B, dtype=torch.int32, device=dev)
+        if buffers is not None:      # caller-owned outputs: identical pointers from call to call let the library replay the
+            Li, n_iters, flags = buffers['Li'], buffers['n_iters'], buffers['flags']       # run as one CUDA graph
+            assert Li.shape == (self.B, max(int(maxIters), 1)) and Li.dtype == torch.float64 and Li.is_contiguous()
+        else:
+            Li = torch.empty((self.B, max(int(maxIters), 1)), dtype=torch.float64, device=dev)
+            n_iters = torch.empty(self.B, dtype=torch.int32, device=dev)
+            flags = torch.empty(self.B, dtype=torch.int32, device=dev)
         self._check(self.lib.vbx_run(
             self._h, _ptr(self.rho), _ptr(self.Phi), _ptr(gamma), _ptr(pi), _ptr(self.n_states),
             float(Fa), float(Fb), float(loopProb), int(maxIters), float(epsilon),

@@ -43,6 +43,15 @@ struct vbx_handle_s {
     int opt_fb_priority = 0;     // 0 = auto (large batches on the fused sweep), 1 = always, 2 = never
     cudaStream_t hi_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // CUDA graph of a whole vbx_run (small batches are launch bound: a run is 41 rounds x up to 12 launches).  The second
+    // call with identical arguments is captured on graph_stream; later identical calls replay the graph with one launch.
+    int opt_graph = 0;           // 0 = auto (plans on the split schedule, i.e. small batches), 1 = always, 2 = never
+    cudaStream_t graph_stream = nullptr;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_key = 0, seen_key = 0;
+    int64_t graph_launches = 0;
+    bool graph_broken = false;
     // NCCL communicator owned by the caller (vbx_attach_comm); ncclAllReduce is resolved from the libnccl the process
     // already uses, so the library has no link-time dependency on NCCL
     void *nccl_comm = nullptr;
@@ -102,6 +111,13 @@ struct Carver {
         return p;
     }
 };
+
+// a captured run is only valid for the plan, workspace and options it was captured with
+void drop_graph(vbx_handle_t h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+    h->graph_key = h->seen_key = 0;
+}
 
 size_t carve(const vbx::Plan &pl, void *base, vbx::Workspace *ws) {
     Carver c(base);
@@ -196,7 +212,10 @@ int vbx_create(int32_t device, vbx_handle_t *out) {
         if (guard.err != cudaSuccess || cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
             cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_g0, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_g1, cudaEventDisableTiming) != cudaSuccess) {
             if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
             if (h->ev_fork) cudaEventDestroy(h->ev_fork);
             delete h;
@@ -214,6 +233,10 @@ int vbx_destroy(vbx_handle_t h) {
     if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
+    if (h->ev_g0) cudaEventDestroy(h->ev_g0);
+    if (h->ev_g1) cudaEventDestroy(h->ev_g1);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return VBX_OK;
@@ -223,6 +246,12 @@ const char *vbx_last_error(vbx_handle_t h) { return h ? h->err.c_str() : "null h
 
 int vbx_set_option(vbx_handle_t h, const char *name, int32_t value) {
     if (!h || !name) return VBX_ERR_ARG;
+    drop_graph(h);
+    if (!strcmp(name, "graph")) {
+        if (value < 0 || value > 2) return fail(h, VBX_ERR_ARG, "graph must be 0 (auto), 1 (always) or 2 (never)");
+        h->opt_graph = value;
+        return VBX_OK;
+    }
     if (!strcmp(name, "fb_states_per_lane")) {
         if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, VBX_ERR_ARG, "fb_states_per_lane must be 0,1,2,4");
         h->opt_fb_spl = value;
@@ -369,6 +398,7 @@ int vbx_plan(vbx_handle_t h, const int64_t *offsets_host, int32_t n_rec, int32_t
     }
     h->planned = h->bound = h->prepared = false;
     h->f64_only = false;
+    drop_graph(h);
     e = cudaMalloc(&h->plan_mem, off);
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(plan)");
     char *base = static_cast<char *>(h->plan_mem);
@@ -462,6 +492,7 @@ int vbx_bind_workspace(vbx_handle_t h, void *workspace, size_t bytes) {
     const size_t mis = reinterpret_cast<uintptr_t>(workspace) & 255;
     char *base = static_cast<char *>(workspace) + (mis ? 256 - mis : 0);
     carve(h->plan, base, &h->ws);
+    drop_graph(h);
     h->bound = true;
     h->prepared = false;
     return VBX_OK;
@@ -610,7 +641,6 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
     if (pl.n_rec == 0) return VBX_OK;
     if (!Li_out || !n_iters_out || !flags_out || !pi_io) return fail(h, VBX_ERR_ARG, "vbx_run: null output pointer");
     if (pl.n_frames && (!rho || !Phi || !gamma_io)) return fail(h, VBX_ERR_ARG, "vbx_run: null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
     vbx::RunParams rp;
     rp.dFa = Fa;
     rp.dFb = Fb;
@@ -628,6 +658,9 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
     rp.noise_c = (double)h->opt_noise_c;
     rp.guard_mult = (double)h->opt_guard_mult;
 
+    // ---- the launch sequence of one run, on stream `st` (directly, or under stream capture) ----
+    auto enqueue = [&](cudaStream_t st) -> int {
+    int rc = 0;
     {
         Timed t(h, st, VBX_K_RUN_INIT);
         rc = counted(h, vbx::launch_run_init(pl, h->ws, gamma_io, n_states, Li_out, n_iters_out, flags_out, max_iters, st), "run_init");
@@ -687,6 +720,64 @@ int vbx_run(vbx_handle_t h, const float *rho, const float *Phi, float *gamma_io,
         }
     }
     return VBX_OK;
+    };   // enqueue
+
+    cudaStream_t user = (cudaStream_t)stream;
+    const bool want_graph = (h->opt_graph == 1 || (h->opt_graph == 0 && pl.split)) && !h->opt_timing && !h->opt_debug_sync &&
+                            !h->graph_broken;
+    if (!want_graph) return enqueue(user);
+    // identity of this call: every argument that ends up inside a kernel parameter
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+    auto bits = [](double d) { uint64_t u; memcpy(&u, &d, 8); return u; };
+    for (const void *p : {(const void *)rho, (const void *)Phi, (const void *)gamma_io, (const void *)pi_io, (const void *)n_states,
+                          (const void *)alpha_io, (const void *)invL_io, (const void *)Li_out, (const void *)n_iters_out,
+                          (const void *)flags_out, (const void *)h->ws.p})
+        mix((uint64_t)(uintptr_t)p);
+    mix(bits(Fa)); mix(bits(Fb)); mix(bits(loop_prob)); mix(bits(epsilon)); mix((uint64_t)max_iters); mix((uint64_t)warm_start);
+    if (key == 0) key = 1;
+    auto replay = [&]() -> int {
+        cudaEventRecord(h->ev_g0, user);
+        cudaStreamWaitEvent(h->graph_stream, h->ev_g0, 0);
+        const cudaError_t e = cudaGraphLaunch(h->graph_exec, h->graph_stream);
+        cudaEventRecord(h->ev_g1, h->graph_stream);
+        cudaStreamWaitEvent(user, h->ev_g1, 0);
+        if (e != cudaSuccess) return cuda_fail(h, e, "cudaGraphLaunch");
+        return VBX_OK;
+    };
+    if (h->graph_exec && key == h->graph_key) {
+        h->launches += h->graph_launches;
+        return replay();
+    }
+    if (key != h->seen_key) {          // first call with these arguments: run directly, capture if they come again
+        h->seen_key = key;
+        return enqueue(user);
+    }
+    // second identical call: capture the launch sequence (relaxed mode: other threads' CUDA calls are not affected)
+    drop_graph(h);
+    h->seen_key = key;
+    const int64_t before = h->launches;
+    if (cudaStreamBeginCapture(h->graph_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        h->graph_broken = true;
+        return enqueue(user);
+    }
+    const int crc = enqueue(h->graph_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->graph_stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (crc != VBX_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        h->launches = before;
+        h->graph_broken = true;           // this handle keeps launching directly
+        return enqueue(user);
+    }
+    cudaGraphDestroy(graph);
+    h->graph_exec = exec;
+    h->graph_key = key;
+    h->graph_launches = h->launches - before;
+    return replay();
 }
 
 int vbx_hard_labels(vbx_handle_t h, const float *gamma, const int32_t *n_states, int32_t *first_out,

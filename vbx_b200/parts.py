@@ -143,7 +143,10 @@ class PartitionedBatch:
         return rho, torch.cat([self._keep(t, main) for t in xn])
 
     # ---- VBx/VBx.py:91-125 --------------------------------------------------------------------
-    def run(self, gamma, pi, alpha=None, invL=None, **kw):
+    def output_buffers(self, maxIters):
+        return None               # the parts allocate their own outputs
+
+    def run(self, gamma, pi, alpha=None, invL=None, buffers=None, **kw):
         main = torch.cuda.current_stream(self.device)
 
         def one(c, fs, rs):
