@@ -752,7 +752,6 @@ def main():
     S = res['S']
     alg_bytes = {   # algorithmic bytes per frame per launch
         'project': 4 * D_RAW + 4 * R_DIM if args.front == 'project' else 4 * D_RAW + 3 * 4 * R_DIM,
-        'prepare': 4 * R_DIM,
         'mstep_partial': 4 * R_DIM + 4 * S,
         'loglik': 4 * R_DIM + 4 * S + 4,
         'forward_backward': 5 * 4 * S + 12,
