@@ -14,6 +14,9 @@ from vbx_b200.api import DER
 from vbx_b200.parts import auto_parts
 from vbx_b200.pipeline import merge_adjacent_labels, rttm_lines
 
+settings.register_profile('repo', derandomize=True, deadline=None, database=None)    # same examples on every run, no .hypothesis/ directory
+settings.load_profile('repo')
+
 LENGTHS = st.lists(st.integers(min_value=1, max_value=20000), min_size=0, max_size=300)
 
 
