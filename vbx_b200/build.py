@@ -22,7 +22,9 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'vbx_b200.h')]
+    # sources only: the objects and ptxas.log written by a build must not make the next call rebuild
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h'))]
+    deps += [os.path.join(HERE, '..', 'include', 'vbx_b200.h'), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
