@@ -14,7 +14,8 @@ from .batch import VbxBatch, run_f64
 
 # Arithmetic of the drop-in call.  'float64' (default): every quantity in float64 on the GPU, reproduces the
 # reference's iteration count and values to ~1e-9 (VBx/vbhmm.py:157 stops on an ELBO step of 1e-6).  'float32': the
-# fast kernels of the batched path (within 1e-4 relative; the stop rule may fire a few iterations early for tiny epsilon).
+# fast kernels of the batched path with their float64 finish near the stop rule: same iteration
+# counts, values within 1e-4 relative (measured 2e-7 on ES2005a), half the latency.
 PRECISION = os.environ.get('VBX_B200_PRECISION', 'float64')
 
 
